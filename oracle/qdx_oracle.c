@@ -1,0 +1,543 @@
+/*
+ * ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product
+ * path (qdax_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load liboracle.so.
+ *
+ * Plain-C restatement of the MAP-Elites generation step of QDax 0.5.1 (reference mounted
+ * read-only at /root/reference; file:line citations below are into that tree), with EVERY
+ * floating-point rounding step spelled out ("QDX-F32 arithmetic spec"):
+ *   - all arithmetic is IEEE-754 binary32, round-to-nearest-even, one rounding per written
+ *     operation; fmaf() is used exactly where written; the file must be compiled with
+ *     -ffp-contract=off and without fast-math;
+ *   - reductions over the genotype / descriptor axis are sequential, left to right;
+ *   - log1p / sin / cos are the polynomial kernels written in this file (the reference calls
+ *     jnp.log1p / jnp.sin / jnp.cos whose last-bit behaviour belongs to jaxlib, which is not
+ *     installable here); they agree with libm to ~1 ulp (tests/test_oracle_cross.py).
+ * The CUDA kernels follow the same spec, which is what makes whole runs bit-comparable.
+ *
+ * The PRNG is jax==0.8.0's Threefry-2x32 in partitionable mode (third-party, un-vendored,
+ * uv.lock:1128-1129): restated from the published algorithm, pinned by the Random123 KATs
+ * and by three values recalled from the JAX documentation (tests/test_oracle_prng.py).
+ * PARITY UNPINNED at the jaxlib boundary for everything else.
+ *
+ * Multi-threaded with OpenMP over the batch; this is also the CPU baseline ("port").
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+
+#define QO_API __attribute__((visibility("default")))
+
+typedef struct { uint32_t a, b; } qo_key;
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* ------------------------------------------------------------------ Threefry-2x32-20 */
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+static inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                uint32_t* o0, uint32_t* o1) {
+    static const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+    uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+    for (int g = 0; g < 5; ++g) {
+        for (int r = 0; r < 4; ++r) {
+            x0 += x1;
+            x1 = rotl32(x1, R[g & 1][r]);
+            x1 ^= x0;
+        }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    *o0 = x0; *o1 = x1;
+}
+
+/* jax.random.split(key, n)[i] in partitionable mode */
+static inline qo_key split_i(qo_key k, uint64_t i) {
+    qo_key o;
+    threefry2x32(k.a, k.b, (uint32_t)(i >> 32), (uint32_t)i, &o.a, &o.b);
+    return o;
+}
+/* random_bits(key, 32, shape)[flat i] */
+static inline uint32_t bits32(qo_key k, uint64_t i) {
+    uint32_t a, b;
+    threefry2x32(k.a, k.b, (uint32_t)(i >> 32), (uint32_t)i, &a, &b);
+    return a ^ b;
+}
+static inline float unit_float(uint32_t bits) { return u2f((bits >> 9) | 0x3F800000u) - 1.0f; }
+/* jnp.clip / jnp.maximum / jnp.minimum written as compares so that NaN propagates (XLA max/min do). */
+static inline float max_nanprop(float x, float lo) { return x < lo ? lo : x; }
+static inline float min_nanprop(float x, float hi) { return x > hi ? hi : x; }
+
+/* ------------------------------------------------------------------ QDX-F32 spec math */
+/* log(t), t > 0 normal.  t = m * 2^e, m in [sqrt(1/2), sqrt(2)); Cephes-style degree-9 kernel. */
+static inline float spec_logf(float t) {
+    uint32_t ix = f2u(t) - 0x3f3504f3u;
+    int e = (int32_t)ix >> 23;
+    float m = u2f((ix & 0x007fffffu) + 0x3f3504f3u);
+    float r = m - 1.0f;
+    float z = r * r;
+    float p = 7.0376836292E-2f;
+    p = fmaf(p, r, -1.1514610310E-1f);
+    p = fmaf(p, r, 1.1676998740E-1f);
+    p = fmaf(p, r, -1.2420140846E-1f);
+    p = fmaf(p, r, 1.4249322787E-1f);
+    p = fmaf(p, r, -1.6668057665E-1f);
+    p = fmaf(p, r, 2.0000714765E-1f);
+    p = fmaf(p, r, -2.4999993993E-1f);
+    p = fmaf(p, r, 3.3333331174E-1f);
+    float y = (p * r) * z;
+    float fe = (float)e;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z, -0.5f, y);
+    float res = r + y;
+    res = fmaf(fe, 0.693359375f, res);
+    return res;
+}
+/* log1p(y) for y in (-1, 0]:  log(t) + (y - (t - 1)) / t  with t = fl(1 + y). */
+static inline float spec_log1pf(float y) {
+    float t = 1.0f + y;
+    if (t == 1.0f) return y;
+    float c = (y - (t - 1.0f)) / t;
+    return spec_logf(t) + c;
+}
+/* XLA ErfInv32 (Giles) with fused Horner steps. */
+static inline float spec_erfinvf(float x) {
+    float w = -spec_log1pf(-(x * x));
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f;
+        p = fmaf(p, w, 3.43273939e-07f);
+        p = fmaf(p, w, -3.5233877e-06f);
+        p = fmaf(p, w, -4.39150654e-06f);
+        p = fmaf(p, w, 0.00021858087f);
+        p = fmaf(p, w, -0.00125372503f);
+        p = fmaf(p, w, -0.00417768164f);
+        p = fmaf(p, w, 0.246640727f);
+        p = fmaf(p, w, 1.50140941f);
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f;
+        p = fmaf(p, w, 0.000100950558f);
+        p = fmaf(p, w, 0.00134934322f);
+        p = fmaf(p, w, -0.00367342844f);
+        p = fmaf(p, w, 0.00573950773f);
+        p = fmaf(p, w, -0.0076224613f);
+        p = fmaf(p, w, 0.00943887047f);
+        p = fmaf(p, w, 1.00167406f);
+        p = fmaf(p, w, 2.83297682f);
+    }
+    if (fabsf(x) == 1.0f) return x * 3.40282347e+38f;
+    return p * x;
+}
+/* jax.random.normal from one 32-bit draw: sqrt(2) * erfinv(max(lo, f*2 + lo)), lo = nextafter(-1, 0). */
+static inline float normal_from_bits(uint32_t bits) {
+    const float lo = -0x1.fffffep-1f;
+    float f = unit_float(bits);
+    float u = f * 2.0f + lo;
+    u = u < lo ? lo : u;
+    return 0x1.6a09e6p+0f * spec_erfinvf(u);
+}
+/* sin and cos: 3-term Cody-Waite reduction by pi/2 (fused), Cephes minimax kernels on [-pi/4, pi/4]. */
+static inline void spec_sincosf(float th, float* s_out, float* c_out) {
+    float q = rintf(th * 0x1.45f306p-1f);
+    float r = fmaf(q, -0x1.921fb6p+0f, th);
+    r = fmaf(q, 0x1.777a5cp-25f, r);
+    r = fmaf(q, 0x1.ee59dap-50f, r);
+    int n = (int)q & 3;
+    float s = r * r;
+    float ps = fmaf(fmaf(-1.9515295891E-4f, s, 8.3321608736E-3f), s, -1.6666654611E-1f);
+    float sr = fmaf(r * s, ps, r);
+    float pc = fmaf(fmaf(2.443315711809948E-5f, s, -1.388731625493765E-3f), s, 4.166664568298827E-2f);
+    float cr = fmaf(s * s, pc, fmaf(s, -0.5f, 1.0f));
+    float sv = (n & 1) ? cr : sr;
+    float cv = (n & 1) ? sr : cr;
+    if (n & 2) sv = -sv;
+    if ((n + 1) & 2) cv = -cv;
+    *s_out = sv; *c_out = cv;
+}
+
+/* ------------------------------------------------------------------ exported probes */
+QO_API int qo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return 0; }
+QO_API int qo_get_threads(void) { return omp_get_max_threads(); }
+
+QO_API int qo_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* out2) {
+    threefry2x32(k0, k1, c0, c1, &out2[0], &out2[1]);
+    return 0;
+}
+QO_API int qo_split(const uint32_t* key, int64_t num, uint32_t* out) {
+    qo_key k = {key[0], key[1]};
+    for (int64_t i = 0; i < num; ++i) { qo_key o = split_i(k, (uint64_t)i); out[2 * i] = o.a; out[2 * i + 1] = o.b; }
+    return 0;
+}
+QO_API int qo_random_bits(const uint32_t* key, int64_t n, uint32_t* out) {
+    qo_key k = {key[0], key[1]};
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) out[i] = bits32(k, (uint64_t)i);
+    return 0;
+}
+QO_API int qo_uniform(const uint32_t* key, int64_t n, float minval, float maxval, float* out) {
+    qo_key k = {key[0], key[1]};
+    float scale = maxval - minval;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float v = unit_float(bits32(k, (uint64_t)i)) * scale + minval;
+        out[i] = v < minval ? minval : v;
+    }
+    return 0;
+}
+QO_API int qo_normal(const uint32_t* key, int64_t n, float* out) {
+    qo_key k = {key[0], key[1]};
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) out[i] = normal_from_bits(bits32(k, (uint64_t)i));
+    return 0;
+}
+/* which: 0 log1p(x in (-1,0]), 1 erfinv, 2 sin, 3 cos */
+QO_API int qo_math_probe(int which, int64_t n, const float* in, float* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        float s, c;
+        switch (which) {
+            case 0: out[i] = spec_log1pf(in[i]); break;
+            case 1: out[i] = spec_erfinvf(in[i]); break;
+            case 2: spec_sincosf(in[i], &s, &c); out[i] = s; break;
+            case 3: spec_sincosf(in[i], &s, &c); out[i] = c; break;
+            default: return -1;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ selection
+ * UniformSelector.select -- qdax/core/emitters/repertoire_selectors/uniform_selector.py:22-62.
+ * `key` is the key handed to select(); :48 splits it once.  jax.random.choice(p):
+ * cum = cumsum(p) (sequential float32), r = cum[-1] * (1 - u), searchsorted(cum, r, 'left'). */
+static int select_indices(const float* fit, int64_t K, qo_key key, int64_t num, int32_t* out) {
+    float* cum = (float*)malloc(sizeof(float) * (size_t)K);
+    if (!cum) return -2;
+    int64_t M = 0;
+    for (int64_t c = 0; c < K; ++c) M += (fit[c] != -INFINITY);
+    if (M == 0) { free(cum); return -3; }  /* p = 0/0 in the reference: undefined */
+    float q = 1.0f / (float)M;
+    float acc = 0.0f;
+    for (int64_t c = 0; c < K; ++c) { acc = acc + ((fit[c] != -INFINITY) ? q : 0.0f); cum[c] = acc; }
+    float total = cum[K - 1];
+    qo_key sub = split_i(key, 1);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < num; ++i) {
+        float u = unit_float(bits32(sub, (uint64_t)i));
+        float r = total * (1.0f - u);
+        int64_t lo = 0, hi = K;                 /* first index with cum[idx] >= r */
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cum[mid] < r) lo = mid + 1; else hi = mid; }
+        out[i] = (int32_t)lo;
+    }
+    free(cum);
+    return 0;
+}
+QO_API int qo_select_indices(const float* fit, int64_t K, const uint32_t* key, int64_t num, int32_t* out) {
+    qo_key k = {key[0], key[1]};
+    return select_indices(fit, K, k, num, out);
+}
+
+/* ------------------------------------------------------------------ isoline variation
+ * qdax/core/emitters/mutation_operators.py:175-226 (single-leaf genotype).
+ * x = (x1 + iso) + (x2 - x1) * line ; clip.  Parents given by index into a (K, D) table when
+ * p1/p2 are non-NULL, else x1/x2 are dense (B, D). */
+static void isoline(const float* x1, const float* x2, const int32_t* p1, const int32_t* p2, int64_t B, int64_t D,
+                    qo_key key, float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,
+                    float* out) {
+    qo_key k_line = split_i(key, 1);             /* :205  key, key_line_noise = split(key) */
+    qo_key k_rest = split_i(key, 0);
+    qo_key k_leaf = split_i(k_rest, 0);          /* :220  split(key, nb_leaves=1)[0] */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < B; ++i) {
+        float line = normal_from_bits(bits32(k_line, (uint64_t)i)) * line_sigma;   /* :207 */
+        const float* a = p1 ? x1 + (int64_t)p1[i] * D : x1 + i * D;
+        const float* b = p2 ? x2 + (int64_t)p2[i] * D : x2 + i * D;
+        for (int64_t d = 0; d < D; ++d) {
+            float iso = normal_from_bits(bits32(k_leaf, (uint64_t)(i * D + d))) * iso_sigma;   /* :210 */
+            float t1 = a[d] + iso;
+            float t2 = b[d] - a[d];
+            float t3 = t2 * line;
+            float x = t1 + t3;                                                             /* :211 */
+            if (has_min) x = max_nanprop(x, minv);                                              /* :214-215 */
+            if (has_max) x = min_nanprop(x, maxv);
+            out[i * D + d] = x;
+        }
+    }
+}
+QO_API int qo_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, const uint32_t* key,
+                                float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,
+                                float* out) {
+    qo_key k = {key[0], key[1]};
+    isoline(x1, x2, NULL, NULL, B, D, k, iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
+    return 0;
+}
+/* MixingEmitter.emit with variation_percentage = 1 -- standard_emitters.py:51-62 */
+QO_API int qo_emit_isoline(const float* rep_g, const float* rep_f, int64_t K, int64_t D, const uint32_t* key, int64_t B,
+                           float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,
+                           float* out, int32_t* p1, int32_t* p2) {
+    qo_key k = {key[0], key[1]};
+    int rc = select_indices(rep_f, K, split_i(k, 0), B, p1);  /* :55-56 */
+    if (rc) return rc;
+    rc = select_indices(rep_f, K, split_i(k, 1), B, p2);      /* :59 */
+    if (rc) return rc;
+    isoline(rep_g, rep_g, p1, p2, B, D, split_i(k, 2), iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ scoring
+ * task 0: arm (qdax/tasks/arm.py:9-38), 1: rastrigin, 2: sphere (qdax/tasks/standard_functions.py:9-24).
+ * Descriptor of rastrigin/sphere = first Dd genes (Dd = 2 in the reference; other Dd is the declared
+ * C4 extension).  */
+static void score_row(int task, const float* p, int64_t D, int64_t Dd, float* f_out, float* desc) {
+    if (task == 0) {
+        float sum = 0.0f;
+        for (int64_t d = 0; d < D; ++d) { float x = min_nanprop(max_nanprop(p[d], 0.0f), 1.0f); sum = (d == 0) ? x : sum + x; }
+        float mean = sum / (float)D;
+        float sq = 0.0f, th = 0.0f, cs = 0.0f, sn = 0.0f;
+        for (int64_t d = 0; d < D; ++d) {
+            float x = min_nanprop(max_nanprop(p[d], 0.0f), 1.0f);
+            float dev = x - mean;
+            float dd = dev * dev;
+            sq = (d == 0) ? dd : sq + dd;
+            float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;     /* 2*pi*x - pi */
+            th = (d == 0) ? ang : th + ang;                      /* cumsum */
+            float s, c;
+            spec_sincosf(th, &s, &c);
+            cs = (d == 0) ? c : cs + c;
+            sn = (d == 0) ? s : sn + s;
+        }
+        float var = sq / (float)D;
+        *f_out = -sqrtf(var);
+        desc[0] = cs / (float)(2 * D) + 0.5f;
+        desc[1] = sn / (float)(2 * D) + 0.5f;
+    } else {
+        float acc = 0.0f;
+        for (int64_t d = 0; d < D; ++d) {
+            float x = p[d] * 10.0f - 5.0f;
+            float term = x * x;
+            if (task == 1) {
+                float s, c;
+                spec_sincosf(0x1.921fb6p+2f * x, &s, &c);
+                term = term - 10.0f * c;
+            }
+            acc = (d == 0) ? term : acc + term;
+        }
+        if (task == 1) acc = (float)(10.0 * (double)D) + acc;
+        *f_out = -acc;
+        for (int64_t j = 0; j < Dd; ++j) desc[j] = p[j];
+    }
+}
+QO_API int qo_score(int task, const float* g, int64_t B, int64_t D, int64_t Dd, float* f, float* desc) {
+    if (task < 0 || task > 2 || (task == 0 && Dd != 2) || Dd > D) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < B; ++i) score_row(task, g + i * D, D, Dd, f + i, desc + i * Dd);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ cell assignment
+ * get_cells_indices -- qdax/core/containers/mapelites_repertoire.py:111-137: brute force,
+ * argmin_k sum_d (x_d - c_kd)^2 (sequential over d), first minimum, NaN counts as minimal. */
+QO_API int qo_cells(const float* desc, int64_t B, int64_t Dd, const float* cent, int64_t K, int32_t* cells) {
+    float* ct = (float*)malloc(sizeof(float) * (size_t)(K * Dd));   /* (Dd, K) transpose */
+    if (!ct) return -2;
+    for (int64_t k = 0; k < K; ++k) for (int64_t j = 0; j < Dd; ++j) ct[j * K + k] = cent[k * Dd + j];
+#pragma omp parallel
+    {
+        enum { BLK = 1024 };
+        float acc[BLK];
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < B; ++i) {
+            const float* x = desc + i * Dd;
+            float best = INFINITY; int64_t bk = -1; int nan_hit = 0;
+            for (int64_t k0 = 0; k0 < K && !nan_hit; k0 += BLK) {
+                int64_t n = K - k0 < BLK ? K - k0 : BLK;
+                for (int64_t j = 0; j < Dd; ++j) {
+                    const float xj = x[j]; const float* c = ct + j * K + k0;
+                    if (j == 0) for (int64_t t = 0; t < n; ++t) { float df = xj - c[t]; acc[t] = df * df; }
+                    else for (int64_t t = 0; t < n; ++t) { float df = xj - c[t]; acc[t] = acc[t] + df * df; }
+                }
+                for (int64_t t = 0; t < n; ++t) {
+                    float v = acc[t];
+                    if (v != v) { bk = k0 + t; nan_hit = 1; break; }     /* first NaN wins */
+                    if (bk < 0 || v < best) { best = v; bk = k0 + t; }
+                }
+            }
+            cells[i] = (int32_t)bk;
+        }
+    }
+    free(ct);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ insertion
+ * MapElitesRepertoire.add -- mapelites_repertoire.py:173-266, given precomputed cells.
+ * tie_break_last = 0: among equal-fitness winners of one cell the FIRST offspring index is stored. */
+QO_API int qo_add(float* rep_g, float* rep_f, float* rep_d, int64_t K, int64_t D, int64_t Dd, const float* g,
+                  const float* f, const float* desc, const int32_t* cells, int64_t B, int tie_break_last,
+                  int32_t* scatter_idx) {
+    float* best = (float*)malloc(sizeof(float) * (size_t)K);
+    int32_t* win = (int32_t*)malloc(sizeof(int32_t) * (size_t)K);
+    if (!best || !win) { free(best); free(win); return -2; }
+    for (int64_t c = 0; c < K; ++c) { best[c] = -INFINITY; win[c] = -1; }
+    for (int64_t i = 0; i < B; ++i) {                       /* segment_max, NaN-propagating  :211-215 */
+        int32_t c = cells[i];
+        if (c < 0 || c >= K) { free(best); free(win); return -1; }
+        float v = f[i], b = best[c];
+        if (b != b) continue;
+        if (v != v || v > b) best[c] = v;
+    }
+    for (int64_t i = 0; i < B; ++i) {
+        int32_t c = cells[i];
+        float fm = (f[i] == best[c]) ? f[i] : -INFINITY;    /* :217-222 */
+        int cond = fm > rep_f[c];                            /* :225-226 strict */
+        if (scatter_idx) scatter_idx[i] = cond ? c : (int32_t)K;   /* :229-231 */
+        if (cond && (tie_break_last || win[c] < 0)) win[c] = (int32_t)i;
+    }
+    for (int64_t c = 0; c < K; ++c) {                        /* .at[idx].set  :234-257 */
+        int32_t i = win[c];
+        if (i < 0) continue;
+        memcpy(rep_g + c * D, g + (int64_t)i * D, sizeof(float) * (size_t)D);
+        rep_f[c] = f[i];
+        memcpy(rep_d + c * Dd, desc + (int64_t)i * Dd, sizeof(float) * (size_t)Dd);
+    }
+    free(best); free(win);
+    return 0;
+}
+
+/* default_qd_metrics -- qdax/utils/metrics.py:74-98.  out = {qd_score, max_fitness, coverage}. */
+QO_API int qo_metrics(const float* rep_f, int64_t K, float qd_offset, float* out3) {
+    double s = 0.0; int64_t filled = 0; float mx = -INFINITY; int nan = 0;
+    for (int64_t c = 0; c < K; ++c) {
+        float v = rep_f[c];
+        if (v != -INFINITY) { s += (double)v; ++filled; }
+        if (v != v) nan = 1; else if (v > mx) mx = v;
+    }
+    out3[0] = (float)s + qd_offset * (float)filled;
+    out3[1] = nan ? NAN : mx;
+    out3[2] = 100.0f * ((float)filled / (float)K);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ driver
+ * lax.scan(MAPElites.scan_update) -- qdax/core/map_elites.py:148-225 with MixingEmitter(pct=1) + isoline.
+ * key chain: scan_update :214 -> update :177 -> ask :241 -> emit ; :181 scoring key (unused by the tasks).
+ * stage_seconds (optional, 4 doubles): emit, score, cells, add+metrics wall-clock. */
+QO_API int qo_map_elites_scan(float* rep_g, float* rep_f, float* rep_d, const float* cent, int64_t K, int64_t D,
+                              int64_t Dd, uint32_t* key_io, int64_t n_iter, int64_t B, int task, float iso_sigma,
+                              float line_sigma, int has_min, float minv, int has_max, float maxv, int tie_break_last,
+                              float qd_offset, float* metrics_out, double* stage_seconds) {
+    float* x = (float*)malloc(sizeof(float) * (size_t)(B * D));
+    float* f = (float*)malloc(sizeof(float) * (size_t)B);
+    float* ds = (float*)malloc(sizeof(float) * (size_t)(B * Dd));
+    int32_t* p1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)B);
+    int32_t* p2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)B);
+    int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * (size_t)B);
+    int rc = (x && f && ds && p1 && p2 && cells) ? 0 : -2;
+    qo_key key = {key_io[0], key_io[1]};
+    double t[4] = {0, 0, 0, 0};
+    for (int64_t it = 0; it < n_iter && rc == 0; ++it) {
+        qo_key sub = split_i(key, 1); key = split_i(key, 0);     /* :214 */
+        qo_key ask_key = split_i(sub, 1);                         /* :177 */
+        qo_key emit_key = split_i(ask_key, 1);                    /* :241 */
+        uint32_t ek[2] = {emit_key.a, emit_key.b};
+        double t0 = omp_get_wtime();
+        rc = qo_emit_isoline(rep_g, rep_f, K, D, ek, B, iso_sigma, line_sigma, has_min, minv, has_max, maxv, x, p1, p2);
+        if (rc) break;
+        double t1 = omp_get_wtime();
+        rc = qo_score(task, x, B, D, Dd, f, ds);
+        if (rc) break;
+        double t2 = omp_get_wtime();
+        rc = qo_cells(ds, B, Dd, cent, K, cells);
+        if (rc) break;
+        double t3 = omp_get_wtime();
+        rc = qo_add(rep_g, rep_f, rep_d, K, D, Dd, x, f, ds, cells, B, tie_break_last, NULL);
+        if (rc) break;
+        if (metrics_out) qo_metrics(rep_f, K, qd_offset, metrics_out + 3 * it);
+        double t4 = omp_get_wtime();
+        t[0] += t1 - t0; t[1] += t2 - t1; t[2] += t3 - t2; t[3] += t4 - t3;
+    }
+    key_io[0] = key.a; key_io[1] = key.b;
+    if (stage_seconds) memcpy(stage_seconds, t, sizeof(t));
+    free(x); free(f); free(ds); free(p1); free(p2); free(cells);
+    return rc;
+}
+
+/* DistributedMAPElites.update -- qdax/core/distributed_map_elites.py:92-161 for R simulated devices.
+ * keys: R*2 words (the per-device key handed to update).  B_dev offspring per device; global offspring
+ * index = rank * B_dev + i (all_gather + concatenate(axis=0), :134-141). */
+QO_API int qo_distributed_update(float* rep_g, float* rep_f, float* rep_d, const float* cent, int64_t K, int64_t D,
+                                 int64_t Dd, const uint32_t* keys, int64_t R, int64_t B_dev, int task,
+                                 float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,
+                                 int tie_break_last, float* g_out, float* f_out, float* d_out, int32_t* cells_out) {
+    int64_t B = R * B_dev;
+    int32_t* p1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)B_dev);
+    int32_t* p2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)B_dev);
+    int rc = (p1 && p2) ? 0 : -2;
+    for (int64_t r = 0; r < R && rc == 0; ++r) {
+        qo_key key = {keys[2 * r], keys[2 * r + 1]};
+        qo_key emit_key = split_i(key, 1);                        /* :124 */
+        uint32_t ek[2] = {emit_key.a, emit_key.b};
+        rc = qo_emit_isoline(rep_g, rep_f, K, D, ek, B_dev, iso_sigma, line_sigma, has_min, minv, has_max, maxv,
+                             g_out + r * B_dev * D, p1, p2);
+        if (rc) break;
+        rc = qo_score(task, g_out + r * B_dev * D, B_dev, D, Dd, f_out + r * B_dev, d_out + r * B_dev * Dd);
+    }
+    if (rc == 0) rc = qo_cells(d_out, B, Dd, cent, K, cells_out);
+    if (rc == 0) rc = qo_add(rep_g, rep_f, rep_d, K, D, Dd, g_out, f_out, d_out, cells_out, B, tie_break_last, NULL);
+    free(p1); free(p2);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ Dominated Novelty Search
+ * _novelty_and_dominated_novelty -- qdax/core/containers/dns_repertoire.py:22-76 (dominated novelty
+ * only; add discards plain novelty, :136).  dn_i = mean of the k smallest sqrt(sum_d (x_id - x_jd)^2)
+ * over j != i with both valid and f_i <= f_j; fewer than k such j -> mean over those; none -> NaN. */
+#define QO_KMAX 32
+QO_API int qo_dns_dominated_novelty(const float* f, const float* desc, int64_t N, int64_t Dd, int k, float* out) {
+    if (k < 1 || k > QO_KMAX) return -1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < N; ++i) {
+        float top[QO_KMAX]; int cnt = 0;
+        float fi = f[i];
+        if (fi == -INFINITY) { out[i] = NAN; continue; }
+        for (int64_t j = 0; j < N; ++j) {
+            if (j == i || f[j] == -INFINITY || !(fi <= f[j])) continue;
+            float acc = 0.0f;
+            for (int64_t d = 0; d < Dd; ++d) { float df = desc[i * Dd + d] - desc[j * Dd + d]; float s = df * df; acc = d ? acc + s : s; }
+            float dist = sqrtf(acc);
+            /* keep k smallest, ascending; NaN/inf distances sort last */
+            if (cnt < k) { int p = cnt++; while (p > 0 && dist < top[p - 1]) { top[p] = top[p - 1]; --p; } top[p] = dist; }
+            else if (dist < top[k - 1]) { int p = k - 1; while (p > 0 && dist < top[p - 1]) { top[p] = top[p - 1]; --p; } top[p] = dist; }
+        }
+        float tot = 0.0f;
+        for (int j = 0; j < cnt; ++j) tot = tot + top[j];
+        out[i] = tot / (float)cnt;          /* 0/0 -> NaN */
+    }
+    return 0;
+}
+/* survivor order = argsort(meta)[::-1]: NaN first, then descending, higher index first among equals (:148). */
+typedef struct { uint32_t key; int32_t idx; } qo_sk;
+static int sk_cmp(const void* a, const void* b) {
+    const qo_sk* x = (const qo_sk*)a; const qo_sk* y = (const qo_sk*)b;
+    if (x->key != y->key) return x->key > y->key ? -1 : 1;
+    return x->idx > y->idx ? -1 : (x->idx < y->idx ? 1 : 0);
+}
+static inline uint32_t order_key(float v) {     /* total order: -inf < ... < -0 == +0 < ... < +inf < NaN */
+    if (v != v) return 0xFFFFFFFFu;
+    uint32_t u = f2u(v == 0.0f ? 0.0f : v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+QO_API int qo_dns_survivors(const float* meta, int64_t N, int64_t P, int32_t* out) {
+    qo_sk* a = (qo_sk*)malloc(sizeof(qo_sk) * (size_t)N);
+    if (!a) return -2;
+    for (int64_t i = 0; i < N; ++i) { a[i].key = order_key(meta[i]); a[i].idx = (int32_t)i; }
+    qsort(a, (size_t)N, sizeof(qo_sk), sk_cmp);
+    for (int64_t i = 0; i < P && i < N; ++i) out[i] = a[i].idx;
+    free(a);
+    return 0;
+}
