@@ -1,0 +1,135 @@
+/*
+ * qdx.h -- C ABI of the B200-native MAP-Elites generation step (libqdx.so).
+ *
+ * This is the drop-in boundary: plain C, device pointers + sizes + a CUDA stream handle (void* =
+ * cudaStream_t), no torch / XLA types.  Every entry point is stream-ordered, non-blocking (except
+ * qdx_workspace_read, which returns host values) and re-entrant; the only mutable state is the
+ * per-repertoire device workspace passed explicitly.  Return value: 0 = ok, > 0 = cudaError_t,
+ * < 0 = QDX_ERR_*.  All arrays are float32 / int32, row-major, C-contiguous, resident in device memory.
+ *
+ * The reference (QDax 0.5.1, /root/reference) has no FFI for this path: the seam is Python-level and
+ * the arithmetic lives in jax/XLA.  Each function below names the reference interface it replaces;
+ * INTEGRATION.md shows the jax.ffi / ctypes binding a maintainer would add on the reference side.
+ */
+#ifndef QDX_H_
+#define QDX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QDX_ERR_ARG (-1)               /* bad argument */
+#define QDX_ERR_UNSUPPORTED (-2)       /* shape outside the fused path; use the unfused entry points */
+#define QDX_ERR_EMPTY_REPERTOIRE (-3)  /* selection from an all-empty repertoire (p = 0/0 in the reference) */
+#define QDX_ERR_BAD_CELL (-4)          /* cell index out of range handed to qdx_offer_cells */
+#define QDX_ERR_BAD_INDEX (-5)         /* winner index outside the offspring buffer handed to qdx_commit */
+
+/* task ids of the fused scoring functions */
+#define QDX_TASK_ID_NONE (-1)
+#define QDX_TASK_ID_ARM 0        /* qdax/tasks/arm.py:9-50 */
+#define QDX_TASK_ID_RASTRIGIN 1  /* qdax/tasks/standard_functions.py:9-15,27-37 */
+#define QDX_TASK_ID_SPHERE 2     /* qdax/tasks/standard_functions.py:18-24,40-48 */
+
+/* Separable grid tessellation (compute_euclidean_centroids, mapelites_repertoire.py:75-108):
+ * the centroid of cell sum_d idx_d * stride[d] is (axes_0[idx_0], axes_1[idx_1], ...).  dd = 0: not a grid.
+ * The fast path is used for descriptors with lo[d] <= x_d <= hi[d]; other rows fall back to brute force. */
+typedef struct qdx_grid_desc {
+    int32_t dd;
+    int32_t n[4];
+    int32_t stride[4];
+    float lo[4];
+    float hi[4];
+    const float* axes; /* device pointer, concatenated axis values (ascending), sum n[d] floats */
+} qdx_grid_desc;
+
+int qdx_version(void);
+
+/* ---- per-repertoire device workspace (selection tables, key chain, 64-bit insertion key table) ---- */
+int qdx_workspace_bytes(int64_t K, int64_t* bytes);
+/* byte offset of the K-entry uint64 insertion-key table inside the workspace (the only part that crosses GPUs) */
+int qdx_workspace_keytab_offset(int64_t K, int64_t* offset);
+int qdx_workspace_init(void* ws, int64_t K, void* stream);
+int qdx_workspace_set_carry_key(void* ws, uint32_t k0, uint32_t k1, void* stream);
+/* blocking read-back of the scan carry key, last metrics {qd_score, max_fitness, coverage, num_added}, error flag */
+int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream);
+
+/* ---- stage (a) set-up.  Replaces the p / cumsum part of UniformSelector.select
+ * (repertoire_selectors/uniform_selector.py:43-45) and the jax.random.split chain of
+ * MAPElites.update/ask (map_elites.py:177,241), scan_update (:214), DistributedMAPElites.update
+ * (distributed_map_elites.py:124), MixingEmitter.emit (standard_emitters.py:55),
+ * isoline_variation (mutation_operators.py:205,220).
+ * key_mode: 0 keep keys | 1 (k0,k1) = key of MAPElites.update | 2 advance the workspace carry key
+ * (scan_update) | 3 (k0,k1) = key of DistributedMAPElites.update | 4 (k0,k1) = key of MixingEmitter.emit */
+int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t key_mode, uint32_t k0, uint32_t k1,
+                       void* stream);
+
+/* ---- stages (a)+(b)[+(c grid)+(d offer)] fused.  Replaces MixingEmitter.emit with variation_percentage=1
+ * (standard_emitters.py:51-62: two UniformSelector.select + isoline_variation), the task scoring function,
+ * and -- when `grid` describes the tessellation and offer != 0 -- get_cells_indices + segment_max
+ * (mapelites_repertoire.py:202-231).  task = QDX_TASK_ID_NONE: variation only (out_genotypes required).
+ * Offspring i of this call has global index idx_base + i (rank * B_dev + i under DistributedMAPElites).
+ * out_genotypes may be NULL when the offspring rows are not needed (winners are re-read by qdx_commit, so
+ * pass NULL only with offer = 0). */
+int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
+                 int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
+                 float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
+                 uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, void* stream);
+
+/* ---- stage (b) standalone: arm_scoring_function / rastrigin_scoring_function / sphere_scoring_function */
+int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
+              float* out_desc, void* stream);
+
+/* ---- stage (c): get_cells_indices (mapelites_repertoire.py:111-137); grid == NULL or grid->dd == 0: brute
+ * force with first-index argmin.  offer != 0 additionally performs the per-cell best-offspring offer. */
+int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const qdx_grid_desc* grid,
+              int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
+              uint32_t idx_base, int32_t first_wins, void* stream);
+
+/* ---- stage (d): MapElitesRepertoire.add (mapelites_repertoire.py:173-266).
+ * qdx_offer_cells: segment_max + tie-break as a packed (fitness-key, index) 64-bit atomicMax per cell.
+ * qdx_commit: scatter of the winners' genotype / fitness / descriptor rows into the repertoire (in place),
+ * key-table reset, and default_qd_metrics (qdax/utils/metrics.py:74-98) -> metrics_out4 (device, optional).
+ * mode 0: offspring rows indexed by (winner index - idx_base).  Modes 1 / 2 split the commit around an exchange
+ * for DistributedMAPElites (distributed_map_elites.py:133-146) when only winners travel: mode 1 copies the
+ * winners owned by [idx_base, idx_base + B) into per-cell staging rows (rep_* = staging; keys kept, no metrics);
+ * mode 2 applies staging rows indexed by cell (off_* = staging), resets the keys and writes the metrics. */
+int qdx_offer_cells(const int32_t* cells, const float* fitness, int64_t B, int64_t K, void* ws, const float* rep_fitness,
+                    uint32_t idx_base, int32_t first_wins, void* stream);
+int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
+               const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
+               float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
+               int32_t mode, void* stream);
+
+/* ---- pieces of the preserved Python surface ---- */
+/* UniformSelector.select index stream for the key handed to select() (uniform_selector.py:48-55) */
+int qdx_select_indices(void* ws, uint32_t k0, uint32_t k1, int64_t num, int32_t* out, void* stream);
+int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, float* out, void* stream);
+/* isoline_variation(x1, x2, key, ...) on dense parents (mutation_operators.py:175-226) */
+int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,
+                          float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval, float* out,
+                          void* stream);
+/* jax.random streams: kind 0 bits (uint32), 1 uniform(minval, maxval), 2 normal */
+int qdx_random(uint32_t k0, uint32_t k1, int64_t n, int32_t kind, float minval, float maxval, void* out, void* stream);
+/* default_qd_metrics -> {qd_score, max_fitness, coverage} */
+int qdx_metrics(const float* rep_fitness, int64_t K, float qd_offset, float* out3, void* stream);
+
+/* ---- stage (e): DominatedNoveltyRepertoire.add (qdax/core/containers/dns_repertoire.py:94-165) including
+ * _novelty_and_dominated_novelty (:22-76).  Candidates = population rows followed by batch rows; outputs are
+ * the new population (separate buffers, sorted exactly like argsort(meta_fitness)[::-1][:P]).
+ * meta_scratch: (P+B) floats (receives the meta fitness), survivors_scratch: P int32 (receives survivor indices). */
+int qdx_dns_add(const float* pop_genotypes, const float* pop_fitness, const float* pop_desc, int64_t P,
+                const float* batch_genotypes, const float* batch_fitness, const float* batch_desc, int64_t B, int64_t D,
+                int32_t desc_dim, int32_t k, float* out_genotypes, float* out_fitness, float* out_desc, float* meta_scratch,
+                int32_t* survivors_scratch, void* stream);
+
+/* ---- host-only helpers (no GPU needed; used by the CPU test-suite) ---- */
+int qdx_host_select_table(int32_t M, float* out_T, int32_t* out_nseg);
+int qdx_host_select_rank(int32_t M, const float* r, int64_t n, int32_t* out_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QDX_H_ */

@@ -1,0 +1,94 @@
+"""ctypes binding of libqdx.so (the C ABI declared in include/qdx.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, we raise.  The library is built
+in-tree by `__graft_entry__.build()` / `make -C qdax_b200/csrc`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqdx.so")
+
+ERRORS = {
+    -1: "QDX_ERR_ARG: bad argument",
+    -2: "QDX_ERR_UNSUPPORTED: shape outside the fused path",
+    -3: "QDX_ERR_EMPTY_REPERTOIRE: selection from an all-empty repertoire",
+    -4: "QDX_ERR_BAD_CELL: cell index out of range",
+    -5: "QDX_ERR_BAD_INDEX: winner index outside the offspring buffer",
+}
+
+
+class QdxError(RuntimeError):
+    def __init__(self, fn: str, rc: int):
+        self.rc = rc
+        msg = ERRORS.get(rc, f"cudaError_t {rc}" if rc > 0 else f"error {rc}")
+        super().__init__(f"{fn} failed: {msg}")
+
+
+class GridDesc(C.Structure):
+    _fields_ = [
+        ("dd", C.c_int32),
+        ("n", C.c_int32 * 4),
+        ("stride", C.c_int32 * 4),
+        ("lo", C.c_float * 4),
+        ("hi", C.c_float * 4),
+        ("axes", C.c_void_p),
+    ]
+
+
+_i32, _i64, _u32, _f32, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_void_p
+
+# name -> argtypes, exactly the prototypes of include/qdx.h
+PROTOTYPES = {
+    "qdx_version": [],
+    "qdx_workspace_bytes": [_i64, C.POINTER(_i64)],
+    "qdx_workspace_keytab_offset": [_i64, C.POINTER(_i64)],
+    "qdx_workspace_init": [_vp, _i64, _vp],
+    "qdx_workspace_set_carry_key": [_vp, _u32, _u32, _vp],
+    "qdx_workspace_read": [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_i32), _vp],
+    "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _vp],
+    "qdx_generate": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _i32,
+                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],
+    "qdx_cells": [_vp, _i64, _i32, _vp, _i64, C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
+    "qdx_offer_cells": [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _i32, _vp],
+    "qdx_commit": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _u32, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
+    "qdx_select_indices": [_vp, _u32, _u32, _i64, _vp, _vp],
+    "qdx_gather_rows": [_vp, _vp, _i64, _i64, _vp, _vp],
+    "qdx_isoline_variation": [_vp, _vp, _i64, _i64, _u32, _u32, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp],
+    "qdx_random": [_u32, _u32, _i64, _i32, _f32, _f32, _vp, _vp],
+    "qdx_metrics": [_vp, _i64, _f32, _vp, _vp],
+    "qdx_dns_add": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "qdx_host_select_table": [_i32, _vp, C.POINTER(_i32)],
+    "qdx_host_select_rank": [_i32, _vp, _i64, _vp],
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load libqdx.so (once).  Raises if the CUDA extension has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C qdax_b200/csrc`. qdax_b200 has no CPU fallback."
+            )
+        h = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = h
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise QdxError(name, rc)

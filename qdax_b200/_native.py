@@ -1,0 +1,283 @@
+"""Torch-tensor-level wrappers over the C ABI (include/qdx.h).  torch supplies device memory and streams only;
+every computation below is a hand-written kernel in libqdx.so.  No CPU fallback: tensors must live on CUDA."""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from qdax_b200 import _lib
+from qdax_b200._lib import GridDesc, call
+
+TASK_IDS = {None: -1, "none": -1, "arm": 0, "rastrigin": 1, "sphere": 2}
+KEYMODE_KEEP, KEYMODE_UPDATE, KEYMODE_SCAN, KEYMODE_DIST_UPDATE, KEYMODE_EMIT = 0, 1, 2, 3, 4
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: qdax_b200 runs on CUDA only (no CPU fallback); got device {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def key_words(key) -> Tuple[int, int]:
+    k = np.asarray(key.cpu() if isinstance(key, torch.Tensor) else key, dtype=np.uint32).reshape(-1)
+    if k.size != 2:
+        raise ValueError("an RNG key is two uint32 words")
+    return int(k[0]), int(k[1])
+
+
+# ------------------------------------------------------------------------------------------ workspace
+class Workspace:
+    """Per-repertoire device workspace: selection segments, key chain, 64-bit insertion key table."""
+
+    def __init__(self, K: int, device: torch.device):
+        n = C.c_int64(0)
+        call("qdx_workspace_bytes", C.c_int64(K), C.byref(n))
+        self.K = K
+        self.buf = torch.empty(n.value, dtype=torch.uint8, device=device)
+        call("qdx_workspace_init", _ptr(self.buf), C.c_int64(K), _stream())
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return _ptr(self.buf)
+
+    def keytab(self) -> torch.Tensor:
+        """int64 view of the K packed 64-bit insertion keys (what the winners-only multi-GPU exchange reduces)."""
+        off = C.c_int64(0)
+        call("qdx_workspace_keytab_offset", C.c_int64(self.K), C.byref(off))
+        return self.buf[off.value: off.value + self.K * 8].view(torch.int64)
+
+    def set_carry_key(self, key) -> None:
+        k0, k1 = key_words(key)
+        call("qdx_workspace_set_carry_key", self.ptr, C.c_uint32(k0), C.c_uint32(k1), _stream())
+
+    def read(self):
+        """Blocking: (carry key (2,) uint32, metrics (4,) float32, error flag)."""
+        ck = (C.c_uint32 * 2)()
+        m = (C.c_float * 4)()
+        err = C.c_int32(0)
+        call("qdx_workspace_read", self.ptr, ck, m, C.byref(err), _stream())
+        return np.array(list(ck), dtype=np.uint32), np.array(list(m), dtype=np.float32), int(err.value)
+
+    def check(self) -> None:
+        _, _, err = self.read()
+        if err != 0:
+            raise _lib.QdxError("device", err)
+
+
+# ------------------------------------------------------------------------------------------ grid detection
+@dataclass
+class Grid:
+    """Separable tessellation detected from a centroid array (compute_euclidean_centroids layout or any
+    product grid).  Keeps the axis tensor alive; `desc` is the ctypes struct handed to the C ABI."""
+
+    n: Tuple[int, ...]
+    stride: Tuple[int, ...]
+    axes: torch.Tensor
+    desc: GridDesc
+
+
+def detect_grid(centroids: torch.Tensor) -> Optional[Grid]:
+    """Host-side, one-off: is `centroids` (K, Dd) a product grid  c[sum_d i_d*stride_d] = (ax_0[i_0], ...)?
+    Returns None when it is not, or when the spacing is too fine for the fast path's exactness guard
+     -- callers then use the brute-force kernel."""
+    c = centroids.detach().cpu().numpy().astype(np.float32)
+    K, Dd = c.shape
+    if Dd < 1 or Dd > 4 or K < 1 or not np.isfinite(c).all():
+        return None
+    axes, idx = [], []
+    for d in range(Dd):
+        ax = np.unique(c[:, d])
+        axes.append(ax)
+        idx.append(np.searchsorted(ax, c[:, d]))
+    n = [len(a) for a in axes]
+    if int(np.prod(n)) != K or sum(n) > 4096 or max(n) > 1024:
+        return None
+    stride = []
+    for d in range(Dd):
+        if n[d] == 1:
+            stride.append(0)
+            continue
+        mask = idx[d] == 1
+        for e in range(Dd):
+            if e != d:
+                mask &= idx[e] == 0
+        ks = np.nonzero(mask)[0]
+        if len(ks) != 1:
+            return None
+        stride.append(int(ks[0]))
+    flat = sum(idx[d].astype(np.int64) * stride[d] for d in range(Dd))
+    if not np.array_equal(flat, np.arange(K)):
+        return None
+    # exactness guard: candidates two steps away must never tie with the nearest after rounding of the sum
+    h_min = min(float(np.min(np.diff(a))) if len(a) > 1 else np.inf for a in axes)
+    span = [float(a[-1] - a[0]) + (float(np.min(np.diff(a))) if len(a) > 1 else 1.0) for a in axes]
+    lo = [float(axes[d][0]) - span[d] for d in range(Dd)]
+    hi = [float(axes[d][-1]) + span[d] for d in range(Dd)]
+    worst = sum((2.0 * s + max(abs(l), abs(u))) ** 2 for s, l, u in zip(span, lo, hi))
+    if np.isfinite(h_min) and 2.0 * h_min * h_min <= 16.0 * worst * 2.0**-23:
+        return None
+    ax_t = torch.from_numpy(np.concatenate(axes).astype(np.float32)).to(centroids.device)
+    gd = GridDesc()
+    gd.dd = Dd
+    for d in range(Dd):
+        gd.n[d], gd.stride[d], gd.lo[d], gd.hi[d] = n[d], stride[d], lo[d], hi[d]
+    gd.axes = ax_t.data_ptr()
+    return Grid(tuple(n), tuple(stride), ax_t, gd)
+
+
+def grid_of(centroids: torch.Tensor) -> Optional[Grid]:
+    """Cached detect_grid (cache lives on the tensor object and is keyed on its storage version)."""
+    cache = getattr(centroids, "_qdx_grid_cache", None)
+    ver = (centroids.data_ptr(), centroids._version, tuple(centroids.shape))
+    if cache is None or cache[0] != ver:
+        cache = (ver, detect_grid(centroids))
+        try:
+            centroids._qdx_grid_cache = cache
+        except AttributeError:
+            pass
+    return cache[1]
+
+
+def _grid_ptr(grid: Optional[Grid]):
+    return C.byref(grid.desc) if grid is not None else C.POINTER(GridDesc)()
+
+
+# ------------------------------------------------------------------------------------------ kernels
+def select_prepare(rep_f: torch.Tensor, ws: Workspace, key_mode: int = KEYMODE_KEEP, key=None) -> None:
+    k0, k1 = key_words(key) if key is not None else (0, 0)
+    call("qdx_select_prepare", _ptr(rep_f), C.c_int64(rep_f.numel()), ws.ptr, C.c_int32(key_mode), C.c_uint32(k0),
+         C.c_uint32(k1), _stream())
+
+
+def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, line_sigma: float, minval, maxval,
+             task: Optional[str], desc_dim: int, grid: Optional[Grid], offer: bool, idx_base: int, first_wins: bool,
+             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None) -> None:
+    K, D = rep_g.shape
+    call("qdx_generate", _ptr(rep_g), _ptr(rep_f), _ptr(centroids), ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B),
+         C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
+         C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim),
+         _grid_ptr(grid), C.c_int32(bool(offer)), C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _ptr(out_g), _ptr(out_f),
+         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), _stream())
+
+
+def score(task: str, g: torch.Tensor, desc_dim: int = 2) -> Tuple[torch.Tensor, torch.Tensor]:
+    g = require_cuda(g, "genotypes")
+    B, D = g.shape
+    f = torch.empty(B, dtype=torch.float32, device=g.device)
+    d = torch.empty(B, desc_dim, dtype=torch.float32, device=g.device)
+    call("qdx_score", C.c_int32(TASK_IDS[task]), _ptr(g), C.c_int64(B), C.c_int64(D), C.c_int32(desc_dim), _ptr(f), _ptr(d), _stream())
+    return f, d
+
+
+def cells(desc: torch.Tensor, centroids: torch.Tensor, grid: Optional[Grid] = None, ws: Optional[Workspace] = None,
+          rep_f: Optional[torch.Tensor] = None, fitness: Optional[torch.Tensor] = None, offer: bool = False,
+          idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, Dd = desc.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=desc.device)
+    call("qdx_cells", _ptr(desc), C.c_int64(B), C.c_int32(Dd), _ptr(centroids), C.c_int64(centroids.shape[0]), _grid_ptr(grid),
+         _ptr(out), C.c_void_p(0) if ws is None else ws.ptr, _ptr(rep_f), _ptr(fitness), C.c_int32(bool(offer)),
+         C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _stream())
+    return out
+
+
+def offer_cells(cell_idx, fitness, ws: Workspace, rep_f, idx_base: int = 0, first_wins: bool = True) -> None:
+    call("qdx_offer_cells", _ptr(cell_idx), _ptr(fitness), C.c_int64(cell_idx.numel()), C.c_int64(ws.K), ws.ptr, _ptr(rep_f),
+         C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _stream())
+
+
+def commit(ws: Workspace, off_g, off_f, off_d, rep_g, rep_f, rep_d, idx_base: int = 0, first_wins: bool = True,
+           qd_offset: float = 0.0, metrics_out: Optional[torch.Tensor] = None, added_cells: Optional[torch.Tensor] = None,
+           mode: int = 0) -> None:
+    K, D = rep_g.shape
+    call("qdx_commit", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int32(rep_d.shape[1]), _ptr(off_g), _ptr(off_f), _ptr(off_d),
+         C.c_uint32(idx_base), C.c_int64(off_f.numel()), C.c_int32(bool(first_wins)), _ptr(rep_g), _ptr(rep_f), _ptr(rep_d),
+         C.c_float(qd_offset), _ptr(metrics_out), _ptr(added_cells), C.c_int32(mode), _stream())
+
+
+def select_indices(ws: Workspace, key, num: int, device) -> torch.Tensor:
+    k0, k1 = key_words(key)
+    out = torch.empty(num, dtype=torch.int32, device=device)
+    call("qdx_select_indices", ws.ptr, C.c_uint32(k0), C.c_uint32(k1), C.c_int64(num), _ptr(out), _stream())
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    src2 = src.reshape(src.shape[0], -1)
+    out = torch.empty((idx.numel(), src2.shape[1]), dtype=torch.float32, device=src.device)
+    call("qdx_gather_rows", _ptr(src2), _ptr(idx), C.c_int64(idx.numel()), C.c_int64(src2.shape[1]), _ptr(out), _stream())
+    return out.reshape((idx.numel(),) + tuple(src.shape[1:]))
+
+
+def isoline_variation(x1, x2, key, iso_sigma, line_sigma, minval=None, maxval=None) -> torch.Tensor:
+    x1 = require_cuda(x1, "x1")
+    x2 = require_cuda(x2, "x2")
+    B = x1.shape[0]
+    D = x1.numel() // max(B, 1)
+    k0, k1 = key_words(key)
+    out = torch.empty_like(x1)
+    call("qdx_isoline_variation", _ptr(x1), _ptr(x2), C.c_int64(B), C.c_int64(D), C.c_uint32(k0), C.c_uint32(k1),
+         C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
+         C.c_int32(maxval is not None), C.c_float(maxval or 0.0), _ptr(out), _stream())
+    return out
+
+
+def random_stream(key, n: int, kind: int, device, minval: float = 0.0, maxval: float = 1.0) -> torch.Tensor:
+    k0, k1 = key_words(key)
+    out = torch.empty(n, dtype=torch.float32 if kind else torch.int32, device=device)
+    call("qdx_random", C.c_uint32(k0), C.c_uint32(k1), C.c_int64(n), C.c_int32(kind), C.c_float(minval), C.c_float(maxval),
+         _ptr(out), _stream())
+    return out
+
+
+def metrics(rep_f: torch.Tensor, qd_offset: float = 0.0) -> torch.Tensor:
+    out = torch.empty(3, dtype=torch.float32, device=rep_f.device)
+    call("qdx_metrics", _ptr(rep_f), C.c_int64(rep_f.numel()), C.c_float(qd_offset), _ptr(out), _stream())
+    return out
+
+
+def dns_add(pop_g, pop_f, pop_d, g, f, d, k: int):
+    """Returns (new genotypes, new fitnesses (P,), new descriptors, meta (N,), survivors (P,))."""
+    P, D = pop_g.shape[0], pop_g.numel() // pop_g.shape[0]
+    B = g.shape[0]
+    dev = pop_g.device
+    out_g = torch.empty_like(pop_g)
+    out_f = torch.empty(P, dtype=torch.float32, device=dev)
+    out_d = torch.empty_like(pop_d)
+    meta = torch.empty(P + B, dtype=torch.float32, device=dev)
+    surv = torch.empty(P, dtype=torch.int32, device=dev)
+    call("qdx_dns_add", _ptr(pop_g), _ptr(pop_f), _ptr(pop_d), C.c_int64(P), _ptr(g), _ptr(f), _ptr(d), C.c_int64(B),
+         C.c_int64(D), C.c_int32(pop_d.shape[1]), C.c_int32(k), _ptr(out_g), _ptr(out_f), _ptr(out_d), _ptr(meta), _ptr(surv),
+         _stream())
+    return out_g, out_f, out_d, meta, surv
+
+
+def host_select_table(M: int) -> Tuple[np.ndarray, int]:
+    out = np.zeros(M, dtype=np.float32)
+    nseg = C.c_int32(0)
+    call("qdx_host_select_table", C.c_int32(M), out.ctypes.data_as(C.c_void_p), C.byref(nseg))
+    return out, int(nseg.value)
+
+
+def host_select_rank(M: int, r: Sequence[float]) -> np.ndarray:
+    r = np.ascontiguousarray(r, dtype=np.float32)
+    out = np.zeros(r.size, dtype=np.int32)
+    call("qdx_host_select_rank", C.c_int32(M), r.ctypes.data_as(C.c_void_p), C.c_int64(r.size), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -1,0 +1,177 @@
+"""Distributed MAP-Elites -- mirrors qdax/core/distributed_map_elites.py:16-244 of the reference.
+
+The reference replicates the repertoire on every device under jax.pmap, lets each device emit and score its own
+shard with its own key, all-gathers (genotypes, fitnesses, descriptors) and applies the identical `add` everywhere.
+Here: one process per GPU (torch.distributed, NCCL over NVLink), same sharding (global offspring index =
+rank * B_dev + i), same per-rank key chain (`key, subkey = split(key)`; emit(subkey); :124-131), two exchanges:
+
+  exchange="allgather"  reference-faithful: the offspring tuples (+ their cells, computed on the shard) are
+                        all-gathered, every rank offers the full batch and commits from the gathered rows.
+  exchange="winners"    only what can change the repertoire travels: each rank offers its shard into its local
+                        64-bit key table, one all-reduce(max) of the K keys elects the global per-cell winners
+                        (the global best of a cell is always a local best), winners' rows are merged through a
+                        K-row staging buffer.  Same repertoire, bit for bit (tests/test_gpu_distributed.py).
+
+Replicas stay bit-identical because the insertion is deterministic: integer atomicMax on packed keys with the
+tie broken on the GLOBAL offspring index.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from qdax_b200 import _native, parallel
+from qdax_b200 import random as qrandom
+from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+from qdax_b200.core.emitters.emitter import EmitterState
+from qdax_b200.core.map_elites import MAPElites
+
+
+class DistributedMAPElites(MAPElites):
+    def __init__(self, *args, exchange: str = "allgather", group=None, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        if exchange not in ("allgather", "winners"):
+            raise ValueError("exchange must be 'allgather' or 'winners'")
+        self._exchange = exchange
+        self._group = group
+        self._dist_buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def init(self, genotypes, centroids, key) -> Tuple[MapElitesRepertoire, Optional[EmitterState], Dict]:
+        """reference :17-90: score the local genotypes with `key` itself (no split, :47), gather, init."""
+        if self._scoring_function is None:
+            raise ValueError("Scoring function is not set.")
+        fitnesses, descriptors, extra_scores = self._scoring_function(genotypes, key)
+        g = parallel.all_gather_rows(genotypes, self._group)
+        f = parallel.all_gather_rows(fitnesses, self._group)
+        d = parallel.all_gather_rows(descriptors, self._group)
+        repertoire = MapElitesRepertoire.init(genotypes=g, fitnesses=f, descriptors=d, centroids=centroids)
+        emitter_state = self._emitter.init(key=key, repertoire=repertoire, genotypes=genotypes, fitnesses=fitnesses,
+                                           descriptors=descriptors, extra_scores=extra_scores)
+        emitter_state = self._emitter.state_update(emitter_state=emitter_state, repertoire=repertoire, genotypes=genotypes,
+                                                   fitnesses=fitnesses, descriptors=descriptors, extra_scores=extra_scores)
+        return repertoire, emitter_state, self._metrics_function(repertoire)
+
+    def _gather_buffers(self, R: int, B: int, D: int, Dd: int, K: int, device) -> Dict[str, torch.Tensor]:
+        k = (R, B, D, Dd, K, str(device))
+        if k not in self._dist_buffers:
+            f32, i32 = torch.float32, torch.int32
+            self._dist_buffers[k] = {
+                "G": torch.empty((R * B, D), dtype=f32, device=device), "F": torch.empty((R * B,), dtype=f32, device=device),
+                "Dn": torch.empty((R * B, Dd), dtype=f32, device=device), "C": torch.empty((R * B,), dtype=i32, device=device),
+                # staging rows by cell for the winners-only exchange: [genotype | descriptor | fitness] per cell
+                "stage": torch.zeros((K, D + Dd + 1), dtype=f32, device=device),
+            }
+        return self._dist_buffers[k]
+
+    def _fused_distributed_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out) -> None:
+        rank, R = parallel.world(self._group)
+        K, D = rep.genotypes.shape
+        B = self._emitter.batch_size
+        Dd = cfg["desc_dim"]
+        dev = rep.genotypes.device
+        buf = self._offspring_buffers(B, D, Dd, dev)
+        gb = self._gather_buffers(R, B, D, Dd, K, dev)
+        ws = rep._workspace()
+        rep_f = rep.fitnesses.reshape(-1)
+        grid = rep._grid()
+        first = rep.tie_break == "first"
+        winners = self._exchange == "winners"
+        base = rank * B
+        _native.select_prepare(rep_f, ws, key_mode, key)
+        _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
+                         cfg["maxval"], cfg["task"], Dd, grid, winners and grid is not None, base, first,
+                         buf["g"], buf["f"], buf["d"], buf["c"])
+        if grid is None:   # cell assignment stays sharded: each rank assigns only its own offspring
+            _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=winners, idx_base=base, first_wins=first, out=buf["c"])
+        if not winners:
+            G = parallel.all_gather_rows(buf["g"], self._group, gb["G"] if R > 1 else None)
+            F = parallel.all_gather_rows(buf["f"], self._group, gb["F"] if R > 1 else None)
+            Dn = parallel.all_gather_rows(buf["d"], self._group, gb["Dn"] if R > 1 else None)
+            Cc = parallel.all_gather_rows(buf["c"], self._group, gb["C"] if R > 1 else None)
+            _native.offer_cells(Cc, F, ws, rep_f, 0, first)
+            _native.commit(ws, G, F, Dn, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
+                           metrics_out=metrics_out)
+            return
+        if R == 1:
+            _native.commit(ws, buf["g"], buf["f"], buf["d"], rep.genotypes, rep_f, rep.descriptors, idx_base=base, first_wins=first,
+                           qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
+            return
+        keytab = ws.keytab()
+        parallel.all_reduce_max_u64_(keytab, self._group)
+        st = gb["stage"]
+        st.zero_()
+        sg, sd, sf = _stage_views(st, D, Dd)
+        _native.commit(ws, buf["g"], buf["f"], buf["d"], sg, sf, sd, idx_base=base, first_wins=first, mode=1)
+        parallel.all_reduce_disjoint_rows_(st, self._group)
+        _native.commit(ws, sg, sf, sd, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
+                       metrics_out=metrics_out, mode=2)
+
+    def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False):
+        """reference :92-161.  `key` is this rank's key (examples/distributed_mapelites.ipynb cell 23:
+        keys = split(key, num_devices))."""
+        if self._scoring_function is None:
+            raise ValueError("Scoring function is not set.")
+        cfg = self._fused_config(repertoire)
+        if cfg is not None:
+            rep = repertoire if donate else repertoire._clone_state()
+            m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
+            self._fused_distributed_generation(rep, cfg, _native.KEYMODE_DIST_UPDATE, key, m)
+            return rep, emitter_state, self._metrics_dict(m)
+        ks = qrandom.split(key)                                             # :124
+        key, subkey = ks[0], ks[1]
+        genotypes, extra_info = self._emitter.emit(repertoire, emitter_state, subkey)
+        ks = qrandom.split(key)                                             # :128
+        key, subkey = ks[0], ks[1]
+        fitnesses, descriptors, extra_scores = self._scoring_function(genotypes, subkey)
+        g = parallel.all_gather_rows(genotypes, self._group)               # :134-141
+        f = parallel.all_gather_rows(fitnesses, self._group)
+        d = parallel.all_gather_rows(descriptors, self._group)
+        repertoire = repertoire.add(g, d, f)                                # :144-146
+        emitter_state = self._emitter.state_update(emitter_state=emitter_state, repertoire=repertoire, genotypes=genotypes,
+                                                   fitnesses=fitnesses, descriptors=descriptors,
+                                                   extra_scores={**extra_scores, **extra_info})
+        return repertoire, emitter_state, self._metrics_function(repertoire)
+
+    def scan(self, carry, length: int, *, donate: bool = False, graph: bool = False):
+        """`num_iterations` updates as in get_distributed_update_fn (:181-244): per iteration
+        `key, subkey = split(key)` (:215) then update(subkey)."""
+        repertoire, emitter_state, key = carry
+        cfg = self._fused_config(repertoire) if self._scoring_function is not None else None
+        rep = repertoire if (donate or cfg is None) else repertoire._clone_state()
+        out = []
+        for _ in range(length):
+            ks = qrandom.split(key)
+            key, subkey = ks[0], ks[1]
+            if cfg is not None:
+                m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
+                self._fused_distributed_generation(rep, cfg, _native.KEYMODE_DIST_UPDATE, subkey, m)
+                out.append(m)
+            else:
+                rep, emitter_state, md = self.update(rep, emitter_state, subkey)
+                out.append(torch.stack([md["qd_score"], md["max_fitness"], md["coverage"], md["coverage"] * 0]))
+        metrics = torch.stack(out) if out else torch.empty((0, 4))
+        return (rep, emitter_state, key), self._metrics_dict(metrics)
+
+    def get_distributed_init_fn(self, centroids, devices: Optional[List[Any]] = None) -> Callable:
+        """reference :163-179.  One process per GPU: the returned function is called by every rank."""
+        return lambda genotypes, key: self.init(genotypes, centroids, key)
+
+    def get_distributed_update_fn(self, num_iterations: int, devices: Optional[List[Any]] = None) -> Callable:
+        """reference :181-244."""
+        def update_fn(repertoire, emitter_state, key):
+            (rep, st, _), metrics = self.scan((repertoire, emitter_state, key), num_iterations)
+            return rep, st, metrics
+        return update_fn
+
+
+def _stage_views(st: torch.Tensor, D: int, Dd: int):
+    """The staging buffer is laid out as three contiguous blocks so each is a valid dense (K, *) array."""
+    K = st.shape[0]
+    flat = st.reshape(-1)
+    sg = flat[: K * D].view(K, D)
+    sd = flat[K * D: K * (D + Dd)].view(K, Dd)
+    sf = flat[K * (D + Dd):].view(K)
+    return sg, sd, sf

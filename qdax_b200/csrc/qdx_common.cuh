@@ -1,0 +1,72 @@
+// Shared device-side structures of the MAP-Elites generation step (B200 / sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "qdx_math.cuh"
+#include "qdx_select.cuh"
+
+#define QDX_TASK_NONE (-1)
+#define QDX_TASK_ARM 0
+#define QDX_TASK_RASTRIGIN 1
+#define QDX_TASK_SPHERE 2
+
+#define QDX_MAX_GRID_DIM 4
+#define QDX_MAX_AXES 4096   // total axis entries (sum of n_d) staged in shared memory
+
+// Keys of one generation, derived from the key handed to MAPElites.update (qdax/core/map_elites.py:177,241;
+// standard_emitters.py:55; uniform_selector.py:48; mutation_operators.py:205,220 under /root/reference).
+struct QdxGenKeys {
+    QdxKey sel1;    // split(split(emit,3)[0])[1]  -> parent-1 uniform draws
+    QdxKey sel2;    // split(split(emit,3)[1])[1]  -> parent-2 uniform draws
+    QdxKey line;    // split(split(emit,3)[2])[1]  -> line noise
+    QdxKey leaf;    // split(split(split(emit,3)[2])[0], 1)[0] -> iso noise
+};
+
+// Device workspace header (one per repertoire); arrays follow at fixed offsets (qdx_ws_* below).
+struct QdxWorkspace {
+    QdxSel sel;             // selection segments of the current repertoire
+    QdxGenKeys keys;        // keys of the current generation (device key chain)
+    QdxKey carry;           // scan carry key (qdax/core/map_elites.py:213-214)
+    float metrics[4];       // qd_score, max_fitness, coverage, num_added
+    uint32_t ticket;        // last-CTA-done counter of the commit kernel
+    int32_t error;          // sticky device-side error flag (e.g. empty repertoire)
+    uint32_t pad[2];
+};
+
+__host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline size_t qdx_ws_occ_offset() { return qdx_align_up(sizeof(QdxWorkspace), 256); }
+__host__ __device__ inline size_t qdx_ws_keytab_offset(int64_t K) {
+    return qdx_align_up(qdx_ws_occ_offset() + sizeof(int32_t) * (size_t)K, 256);
+}
+__host__ __device__ inline size_t qdx_ws_total_bytes(int64_t K) {
+    return qdx_align_up(qdx_ws_keytab_offset(K) + sizeof(unsigned long long) * (size_t)K, 256);
+}
+__host__ __device__ inline int32_t* qdx_ws_occ(void* ws) { return (int32_t*)((char*)ws + qdx_ws_occ_offset()); }
+__host__ __device__ inline unsigned long long* qdx_ws_keytab(void* ws, int64_t K) {
+    return (unsigned long long*)((char*)ws + qdx_ws_keytab_offset(K));
+}
+
+// Separable ("Euclidean grid") tessellation: centroid of cell sum_d idx_d*stride_d is (axis_0[idx_0], ...).
+struct QdxGrid {
+    int32_t dd;                          // 0 = not a grid (brute force)
+    int32_t n[QDX_MAX_GRID_DIM];
+    int32_t stride[QDX_MAX_GRID_DIM];
+    int32_t off[QDX_MAX_GRID_DIM];       // offset of axis d inside `axes`
+    float lo[QDX_MAX_GRID_DIM];          // fast path valid for lo <= x_d <= hi (else exact brute force per row)
+    float hi[QDX_MAX_GRID_DIM];
+    const float* axes;                   // device, sum n_d floats
+    int32_t total_axes;
+};
+
+// Packed 64-bit insertion key: (order_key(fitness) << 32) | (first_wins ? ~idx : idx); 0 = empty slot.
+QDX_DEV unsigned long long qdx_pack_key(float f, uint32_t idx, int first_wins) {
+    return ((unsigned long long)qdx_order_key(f) << 32) | (unsigned long long)(first_wins ? ~idx : idx);
+}
+
+// Offer offspring `idx` with fitness f to cell c (MapElitesRepertoire.add, mapelites_repertoire.py:211-231):
+// only candidates that can change the outcome touch the table (NaN poisons its cell; f <= current never wins
+// and never blocks a winner because any winner has f > current >= f).
+QDX_DEV void qdx_offer(unsigned long long* keytab, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
+    const float cur = __ldg(rep_f + c);
+    if ((f != f) || f > cur) atomicMax(keytab + c, qdx_pack_key(f, idx, first_wins));
+}

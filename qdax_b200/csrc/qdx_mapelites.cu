@@ -1,0 +1,969 @@
+// MAP-Elites generation step on B200 (sm_100a): hand-written kernels behind the C ABI of include/qdx.h.
+//
+//   prepare   occupancy scan -> occupied-cell list + selection segments; device-side key chain
+//   generate  parent sampling + Iso+LineDD variation (Threefry-2x32, counter-based) + fused task scoring
+//             + grid cell assignment + packed 64-bit atomicMax offer          (stages a, b, c-grid, d-offer)
+//   cells     brute-force nearest centroid, first-index argmin, + offer       (stage c, d-offer)
+//   commit    per-cell winner row copy into the HBM-resident repertoire + QD metrics  (stage d)
+//
+// Layout: everything float32 row-major; a warp owns a tile of 32 consecutive offspring rows staged in shared
+// memory as the exact global-memory image of those rows, so the tile leaves the SM with ONE bulk async copy
+// (cp.async.bulk shared->global, the TMA engine) while the warp moves on.  Work inside a tile has two shapes:
+// gene-parallel (RNG + variation: lanes stride over float4 quads of the tile, parents gathered with 128-bit
+// coalesced loads) and row-serial (scoring: lane = row, sequential float32 reductions exactly as the spec).
+//
+// Reference semantics being reproduced (under /root/reference): qdax/core/map_elites.py:148-225,
+// qdax/core/emitters/standard_emitters.py:27-82, .../repertoire_selectors/uniform_selector.py:22-62,
+// qdax/core/emitters/mutation_operators.py:175-226, qdax/tasks/arm.py:9-50,
+// qdax/tasks/standard_functions.py:9-48, qdax/core/containers/mapelites_repertoire.py:111-266,
+// qdax/utils/metrics.py:74-98.
+#include "qdx_common.cuh"
+#include "../../include/qdx.h"
+
+#define QDX_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// =====================================================================================================
+// prepare
+// =====================================================================================================
+__device__ void qdx_derive_gen_keys(QdxKey emit, QdxGenKeys* out) {
+    QdxKey e0 = qdx_split(emit, 0), e1 = qdx_split(emit, 1), kv = qdx_split(emit, 2);   // standard_emitters.py:55
+    out->sel1 = qdx_split(e0, 1);                                                        // uniform_selector.py:48
+    out->sel2 = qdx_split(e1, 1);
+    out->line = qdx_split(kv, 1);                                                        // mutation_operators.py:205
+    out->leaf = qdx_split(qdx_split(kv, 0), 0);                                          // :220 (one leaf)
+}
+
+// key_mode: 0 keep keys; 1 `key` = key of MAPElites.update; 2 scan step on ws->carry; 3 `key` = key of
+// DistributedMAPElites.update; 4 `key` = emit key.
+__global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restrict__ rep_f, int64_t K, void* ws_raw,
+                                                           QdxKey key, int key_mode) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    int32_t* occ = qdx_ws_occ(ws_raw);
+    __shared__ int32_t s_warp[32];
+    __shared__ int32_t s_total;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+
+    if (t == 32 && key_mode != 0) {      // key chain on warp 1, overlapping the scan
+        if (key_mode == 2) { QdxKey c = ws->carry; key = qdx_split(c, 1); ws->carry = qdx_split(c, 0); }  // map_elites.py:214
+        QdxKey emit = key;
+        if (key_mode == 1 || key_mode == 2) emit = qdx_split(qdx_split(key, 1), 1);                         // :177, :241
+        else if (key_mode == 3) emit = qdx_split(key, 1);                                // distributed_map_elites.py:124
+        qdx_derive_gen_keys(emit, &ws->keys);
+    }
+
+    const int64_t chunk = (K + blockDim.x - 1) / blockDim.x;
+    const int64_t lo = (int64_t)t * chunk, hi = lo + chunk < K ? lo + chunk : K;
+    int32_t cnt = 0;
+    for (int64_t c = lo; c < hi; ++c) cnt += (rep_f[c] != -INFINITY);
+    int32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int32_t v = s_warp[lane], x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        s_warp[lane] = x - v;
+        if (lane == 31) s_total = x;
+    }
+    __syncthreads();
+    int32_t pos = s_warp[w] + incl - cnt;
+    for (int64_t c = lo; c < hi; ++c) if (rep_f[c] != -INFINITY) occ[pos++] = (int32_t)c;
+    if (t == 0) {
+        const int32_t M = s_total;
+        if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
+        if (M <= 0 || ws->sel.nseg <= 0) ws->error = QDX_ERR_EMPTY_REPERTOIRE;
+    }
+}
+
+// =====================================================================================================
+// grid cell assignment (exactly equal to the brute-force argmin)
+// =====================================================================================================
+template <int DD>
+__device__ __forceinline__ int32_t qdx_cell_bruteforce_row(const float* x, const float* __restrict__ cent, int64_t K) {
+    float best = INFINITY; int32_t bk = 0;
+    for (int64_t k = 0; k < K; ++k) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DD; ++d) { float df = x[d] - cent[k * DD + d]; float s = df * df; acc = d ? acc + s : s; }
+        if (acc != acc) return (int32_t)k;
+        if (acc < best) { best = acc; bk = (int32_t)k; }
+    }
+    return bk;
+}
+
+template <int DD>
+__device__ __forceinline__ int32_t qdx_grid_cell(const float* x, const QdxGrid& g, const float* s_axes,
+                                                 const float* __restrict__ cent, int64_t K) {
+    int32_t ci[DD][3]; float ca[DD][3]; int32_t cn[DD];
+#pragma unroll
+    for (int d = 0; d < DD; ++d) {
+        const float xd = x[d];
+        if (!(fabsf(xd) <= 3.40282347e+38f)) return 0;           // NaN / inf: every distance NaN or inf -> index 0
+        if (xd < g.lo[d] || xd > g.hi[d]) return qdx_cell_bruteforce_row<DD>(x, cent, K);   // rare, exact
+        const float* ax = s_axes + g.off[d];
+        int lo = 0, hi = g.n[d];                                 // lower_bound: first ax[p] >= xd
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ax[mid] < xd) lo = mid + 1; else hi = mid; }
+        int c0 = lo - 1 < 0 ? 0 : lo - 1;
+        int c1 = lo + 1 > g.n[d] - 1 ? g.n[d] - 1 : lo + 1;
+        cn[d] = c1 - c0 + 1;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const int c = (c0 + m <= c1) ? c0 + m : c1; float df = xd - ax[c]; ci[d][m] = c; ca[d][m] = df * df; }
+    }
+    float best = INFINITY; int32_t bflat = 0x7fffffff;
+    // all 3^DD candidate cells, compile-time indices (registers only); lowest flat index wins ties
+#pragma unroll
+    for (int m0 = 0; m0 < 3; ++m0)
+#pragma unroll
+        for (int m1 = 0; m1 < (DD > 1 ? 3 : 1); ++m1)
+#pragma unroll
+            for (int m2 = 0; m2 < (DD > 2 ? 3 : 1); ++m2)
+#pragma unroll
+                for (int m3 = 0; m3 < (DD > 3 ? 3 : 1); ++m3) {
+                    bool ok = m0 < cn[0];
+                    float acc = ca[0][m0]; int32_t flat = ci[0][m0] * g.stride[0];
+                    if (DD > 1) { ok = ok && m1 < cn[DD > 1 ? 1 : 0]; acc = acc + ca[DD > 1 ? 1 : 0][m1]; flat += ci[DD > 1 ? 1 : 0][m1] * g.stride[1]; }
+                    if (DD > 2) { ok = ok && m2 < cn[DD > 2 ? 2 : 0]; acc = acc + ca[DD > 2 ? 2 : 0][m2]; flat += ci[DD > 2 ? 2 : 0][m2] * g.stride[2]; }
+                    if (DD > 3) { ok = ok && m3 < cn[DD > 3 ? 3 : 0]; acc = acc + ca[DD > 3 ? 3 : 0][m3]; flat += ci[DD > 3 ? 3 : 0][m3] * g.stride[3]; }
+                    if (ok && (acc < best || (acc == best && flat < bflat))) { best = acc; bflat = flat; }
+                }
+    return bflat;
+}
+
+// =====================================================================================================
+// generate
+// =====================================================================================================
+struct QdxGenParams {
+    const float* rep_g; const float* rep_f; const float* centroids;
+    void* ws;
+    int64_t B; int64_t K; int32_t D; int32_t DC;     // DC = genes per staged chunk (multiple of 4)
+    int32_t DS;                                       // shared-memory row stride in floats (DS/4 odd: conflict-free LDS.128)
+    float iso_sigma, line_sigma; int32_t has_min, has_max; float minv, maxv;
+    float* out_g; float* out_f; float* out_d; int32_t* out_cell; int32_t* out_p1; int32_t* out_p2;
+    int32_t desc_dim;
+    QdxGrid grid;
+    int32_t offer; uint32_t idx_base; int32_t first_wins;
+};
+
+QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 :: "l"(gptr), "r"((uint32_t)__cvta_generic_to_shared(sptr)), "r"(bytes) : "memory");
+}
+
+constexpr int QDX_GEN_WARPS = 4;
+
+template <int TASK, int GRID_DD>
+__global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const QdxGenParams p) {
+    extern __shared__ __align__(128) float s_tiles[];
+    __shared__ QdxSeg s_seg[QDX_MAX_SEG];
+    __shared__ float s_last[QDX_MAX_SEG];
+    __shared__ float s_axes[GRID_DD > 0 ? QDX_MAX_AXES : 1];
+
+    const QdxWorkspace* ws = (const QdxWorkspace*)p.ws;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nseg = ws->sel.nseg;
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
+    if (GRID_DD > 0) for (int i = threadIdx.x; i < p.grid.total_axes; i += blockDim.x) s_axes[i] = p.grid.axes[i];
+    __syncthreads();
+    if (nseg <= 0) return;     // empty repertoire: error flag already raised by prepare
+
+    const int32_t D = p.D, DC = p.DC, DS = p.DS;
+    float* tile = s_tiles + (size_t)warp * 32 * DS;
+    const int64_t row0 = ((int64_t)blockIdx.x * QDX_GEN_WARPS + warp) * 32;
+    if (row0 >= p.B) return;
+    const int64_t row = row0 + lane;
+    const bool valid = row < p.B;
+    const int nrows = (p.B - row0) < 32 ? (int)(p.B - row0) : 32;
+    const QdxGenKeys keys = ws->keys;
+    const int32_t* __restrict__ occ = qdx_ws_occ(p.ws);
+    const float total = ws->sel.total;
+
+    // ---- phase 0: parents + line noise, lane = row --------------------------------------------------
+    int32_t p1 = 0, p2 = 0; float line = 0.0f;
+    if (valid) {
+        float u1 = qdx_unit_float(qdx_bits32(keys.sel1, (uint64_t)row));
+        float u2 = qdx_unit_float(qdx_bits32(keys.sel2, (uint64_t)row));
+        p1 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u1)) - 1];
+        p2 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u2)) - 1];
+        line = qdx_normal_from_bits(qdx_bits32(keys.line, (uint64_t)row)) * p.line_sigma;
+        if (p.out_p1) p.out_p1[row] = p1;
+        if (p.out_p2) p.out_p2[row] = p2;
+    }
+
+    // row-serial accumulators (TASK-dependent), carried across chunks
+    float acc0 = 0.0f;
+    const int nchunks = (D + DC - 1) / DC;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int d0 = ch * DC;
+        const int dc = (D - d0) < DC ? (D - d0) : DC;     // genes in this chunk (multiple of 4)
+        const int q = dc >> 2;
+        // ---- phase 1: gene-parallel variation over the tile ---------------------------------------------
+        {
+            int r = 0, dq = lane;
+            while (dq >= q) { dq -= q; ++r; }
+            const int total_quads = nrows * q;
+            for (int qi = lane; qi < ((total_quads + 31) & ~31); qi += 32) {
+                const bool act = qi < total_quads;
+                const int rr = act ? r : 0;
+                const int32_t pa = __shfl_sync(0xffffffffu, p1, rr);
+                const int32_t pb = __shfl_sync(0xffffffffu, p2, rr);
+                const float ln = __shfl_sync(0xffffffffu, line, rr);
+                if (act) {
+                    const int d = d0 + (dq << 2);
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pa * D + d));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pb * D + d));
+                    const uint64_t ctr = (uint64_t)(row0 + rr) * (uint64_t)D + (uint64_t)d;
+                    float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, xv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float iso = qdx_normal_from_bits(qdx_bits32(keys.leaf, ctr + j)) * p.iso_sigma;
+                        float t1 = av[j] + iso;
+                        float t2 = bv[j] - av[j];
+                        float t3 = t2 * ln;
+                        float x = t1 + t3;                                  // mutation_operators.py:211
+                        if (p.has_min) x = qdx_max_nanprop(x, p.minv);      // :214-215
+                        if (p.has_max) x = qdx_min_nanprop(x, p.maxv);
+                        xv[j] = x;
+                    }
+                    *reinterpret_cast<float4*>(tile + rr * DS + (dq << 2)) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                }
+                dq += 32; while (dq >= q) { dq -= q; ++r; }
+            }
+        }
+        // ---- phase 3 (issued early): tile -> global through the bulk-copy engine ------------------------
+        // writers make their generic-proxy stores visible to the async proxy, then the warp syncs, then issue
+        if (p.out_g) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (p.out_g) {
+            if (DS == D) {      // tile is the exact global image of nrows consecutive rows: one bulk copy
+                if (lane == 0) qdx_bulk_store(p.out_g + row0 * D, tile, (uint32_t)(nrows * D * 4));
+            } else if (valid) {
+                qdx_bulk_store(p.out_g + row * D + d0, tile + lane * DS, (uint32_t)(dc * 4));
+            }
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+        // ---- phase 2: row-serial scoring, lane = row ---------------------------------------------------
+        if (TASK != QDX_TASK_NONE && valid) {
+            const float* xr = tile + lane * DS;
+            if (TASK == QDX_TASK_ARM) {        // single chunk guaranteed by the launcher
+                float sum = 0.0f;
+                for (int d = 0; d < dc; d += 4) {
+                    float4 v = *reinterpret_cast<const float4*>(xr + d);
+                    float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float x = qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f);
+                        sum = (d + j == 0) ? x : sum + x;
+                    }
+                }
+                const float mean = __fdiv_rn(sum, (float)D);
+                float sq = 0.0f, th = 0.0f, cs = 0.0f, sn = 0.0f;
+                for (int d = 0; d < dc; d += 4) {
+                    float4 v = *reinterpret_cast<const float4*>(xr + d);
+                    float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float x = qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f);
+                        float dev = x - mean;
+                        float dd = dev * dev;
+                        float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;
+                        float s, c;
+                        if (d + j == 0) { sq = dd; th = ang; qdx_sincosf(th, s, c); cs = c; sn = s; }
+                        else { sq = sq + dd; th = th + ang; qdx_sincosf(th, s, c); cs = cs + c; sn = sn + s; }
+                    }
+                }
+                const float fit = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
+                const float dx = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
+                const float dy = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
+                p.out_f[row] = fit;
+                reinterpret_cast<float2*>(p.out_d)[row] = make_float2(dx, dy);
+                if (GRID_DD > 0) {
+                    float xd[QDX_MAX_GRID_DIM] = {dx, dy, 0.0f, 0.0f};
+                    const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
+                    if (p.out_cell) p.out_cell[row] = cell;
+                    if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                }
+            } else {
+                for (int d = 0; d < dc; d += 4) {
+                    float4 v = *reinterpret_cast<const float4*>(xr + d);
+                    float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float x = xs[j] * 10.0f - 5.0f;
+                        float term = x * x;
+                        if (TASK == QDX_TASK_RASTRIGIN) {
+                            float s, c;
+                            qdx_sincosf(0x1.921fb6p+2f * x, s, c);
+                            term = term - 10.0f * c;
+                        }
+                        acc0 = (d0 + d + j == 0) ? term : acc0 + term;
+                    }
+                }
+                if (ch == 0) {
+                    for (int j = 0; j < p.desc_dim; ++j) p.out_d[row * p.desc_dim + j] = xr[j];   // desc = first genes
+                }
+                if (ch == nchunks - 1) {
+                    float f = acc0;
+                    if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
+                    const float fit = -f;
+                    p.out_f[row] = fit;
+                    if (GRID_DD > 0) {
+                        float xd[QDX_MAX_GRID_DIM];
+#pragma unroll
+                        for (int j = 0; j < (GRID_DD == 0 ? 1 : GRID_DD); ++j) xd[j] = p.out_d[row * p.desc_dim + j];
+                        const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
+                        if (p.out_cell) p.out_cell[row] = cell;
+                        if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                    }
+                }
+            }
+        }
+        // the tile is rewritten by the next chunk: wait until the bulk engine has finished READING it
+        if (p.out_g) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// standalone scoring:  (B, D) genotypes -> fitness (B,), descriptors (B, Dd)
+// =====================================================================================================
+template <int TASK>
+__global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict__ g, int64_t B, int32_t D, int32_t desc_dim,
+                                                        float* __restrict__ out_f, float* __restrict__ out_d) {
+    // One warp per 32-row tile; genotype chunks are staged row-major in shared memory with a coalesced
+    // cooperative copy, then consumed row-serially (lane = row) in the canonical left-to-right order.
+    extern __shared__ __align__(128) float s_tiles[];
+    constexpr int DC = 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = s_tiles + (size_t)warp * 32 * (DC + 1);
+    const int64_t row0 = ((int64_t)blockIdx.x * 4 + warp) * 32;
+    if (row0 >= B) return;
+    const int64_t row = row0 + lane;
+    const bool valid = row < B;
+    const int nrows = (B - row0) < 32 ? (int)(B - row0) : 32;
+    const int npass = (TASK == QDX_TASK_ARM) ? 2 : 1;
+    float sum = 0.0f, mean = 0.0f, sq = 0.0f, th = 0.0f, cs = 0.0f, sn = 0.0f, acc = 0.0f;
+    for (int pass = 0; pass < npass; ++pass) {
+        for (int d0 = 0; d0 < D; d0 += DC) {
+            const int dc = (D - d0) < DC ? (D - d0) : DC;
+            __syncwarp();
+            for (int i = lane; i < nrows * dc; i += 32) {       // coalesced: consecutive lanes -> consecutive genes
+                const int r = i / dc, d = i - r * dc;
+                tile[r * (DC + 1) + d] = g[(row0 + r) * D + d0 + d];
+            }
+            __syncwarp();
+            if (!valid) continue;
+            const float* xr = tile + lane * (DC + 1);
+            if (TASK == QDX_TASK_ARM) {
+                if (pass == 0) {
+                    for (int d = 0; d < dc; ++d) {
+                        float x = qdx_min_nanprop(qdx_max_nanprop(xr[d], 0.0f), 1.0f);
+                        sum = (d0 + d == 0) ? x : sum + x;
+                    }
+                } else {
+                    for (int d = 0; d < dc; ++d) {
+                        float x = qdx_min_nanprop(qdx_max_nanprop(xr[d], 0.0f), 1.0f);
+                        float dev = x - mean;
+                        float dd = dev * dev;
+                        float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;
+                        float s, c;
+                        if (d0 + d == 0) { sq = dd; th = ang; qdx_sincosf(th, s, c); cs = c; sn = s; }
+                        else { sq = sq + dd; th = th + ang; qdx_sincosf(th, s, c); cs = cs + c; sn = sn + s; }
+                    }
+                }
+            } else {
+                for (int d = 0; d < dc; ++d) {
+                    float x = xr[d] * 10.0f - 5.0f;
+                    float term = x * x;
+                    if (TASK == QDX_TASK_RASTRIGIN) { float s, c; qdx_sincosf(0x1.921fb6p+2f * x, s, c); term = term - 10.0f * c; }
+                    acc = (d0 + d == 0) ? term : acc + term;
+                    if (d0 + d < desc_dim) out_d[row * desc_dim + d0 + d] = xr[d];
+                }
+            }
+        }
+        if (TASK == QDX_TASK_ARM && pass == 0) mean = __fdiv_rn(sum, (float)D);
+    }
+    if (!valid) return;
+    if (TASK == QDX_TASK_ARM) {
+        out_f[row] = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
+        out_d[row * 2 + 0] = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
+        out_d[row * 2 + 1] = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
+    } else {
+        float f = acc;
+        if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
+        out_f[row] = -f;
+    }
+}
+
+// =====================================================================================================
+// brute-force cell assignment (+ optional offer)
+// =====================================================================================================
+// Each thread owns one descriptor row; centroids stream through shared memory in tiles (broadcast LDS).
+// Inner loop per 16-centroid group keeps only a running minimum (FMNMX); the group is rescanned for the
+// FIRST index only when it improves the row's best, which happens O(log K) times per row.
+template <int DD>
+__global__ void __launch_bounds__(256) qdx_cells_bf_kernel(const float* __restrict__ desc, int64_t B,
+                                                           const float* __restrict__ cent, int64_t K,
+                                                           int32_t* __restrict__ cells, void* ws, const float* rep_f,
+                                                           const float* __restrict__ fit, int32_t offer,
+                                                           uint32_t idx_base, int32_t first_wins) {
+    extern __shared__ __align__(16) float s_cent[];
+    constexpr int TILE = 2048;                  // centroids per shared-memory tile
+    constexpr int GROUP = 16;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = row < B;
+    float x[DD];
+    bool finite = true;
+#pragma unroll
+    for (int d = 0; d < DD; ++d) { x[d] = valid ? desc[row * DD + d] : 0.0f; finite = finite && (fabsf(x[d]) <= 3.40282347e+38f); }
+    float best = INFINITY; int32_t bk = 0;
+    for (int64_t k0 = 0; k0 < K; k0 += TILE) {
+        const int n = (K - k0) < TILE ? (int)(K - k0) : TILE;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * DD; i += blockDim.x) s_cent[i] = cent[k0 * DD + i];
+        for (int i = n * DD + threadIdx.x; i < ((n + GROUP - 1) / GROUP) * GROUP * DD; i += blockDim.x) s_cent[i] = INFINITY;  // pad
+        __syncthreads();
+        if (!valid || !finite) continue;
+        for (int g0 = 0; g0 < n; g0 += GROUP) {
+            float gmin = INFINITY;
+#pragma unroll
+            for (int t = 0; t < GROUP; ++t) {
+                float acc;
+#pragma unroll
+                for (int d = 0; d < DD; ++d) { float df = x[d] - s_cent[(g0 + t) * DD + d]; float s = df * df; acc = d ? acc + s : s; }
+                gmin = fminf(gmin, acc);       // padded centroids give inf/NaN-free inf; fminf drops NaN (none here)
+            }
+            if (gmin < best) {
+                best = gmin;
+                for (int t = 0; t < GROUP; ++t) {
+                    float acc;
+#pragma unroll
+                    for (int d = 0; d < DD; ++d) { float df = x[d] - s_cent[(g0 + t) * DD + d]; float s = df * df; acc = d ? acc + s : s; }
+                    if (acc == gmin) { bk = (int32_t)(k0 + g0 + t); break; }
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    // non-finite descriptor: every distance is inf or NaN -> argmin = 0 (first inf / first NaN), centroids finite
+    cells[row] = bk;
+    if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, bk, fit[row], idx_base + (uint32_t)row, first_wins);
+}
+
+// generic descriptor dimension (runtime Dd): same algorithm, descriptor row kept in shared memory
+__global__ void __launch_bounds__(128) qdx_cells_bf_generic_kernel(const float* __restrict__ desc, int64_t B, int32_t Dd,
+                                                                   const float* __restrict__ cent, int64_t K,
+                                                                   int32_t* __restrict__ cells, void* ws, const float* rep_f,
+                                                                   const float* __restrict__ fit, int32_t offer,
+                                                                   uint32_t idx_base, int32_t first_wins) {
+    // one warp per descriptor row: lanes split the centroids, each computes full sequential-over-d distances
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= B) return;
+    const float* x = desc + row * Dd;
+    float best = INFINITY; int64_t bk = 0x7fffffff; bool any_nan = false; int64_t nan_k = 0x7fffffff;
+    for (int64_t k = lane; k < K; k += 32) {
+        const float* c = cent + k * Dd;
+        float acc = 0.0f;
+        for (int d = 0; d < Dd; ++d) { float df = x[d] - c[d]; float s = df * df; acc = d ? acc + s : s; }
+        if (acc != acc) { if (!any_nan) { any_nan = true; nan_k = k; } }
+        else if (acc < best) { best = acc; bk = k; }
+    }
+    // lexicographic (dist, k) min across lanes; NaN wins with its smallest index
+    for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        long long ok = __shfl_xor_sync(0xffffffffu, (long long)bk, o);
+        long long on = __shfl_xor_sync(0xffffffffu, (long long)nan_k, o);
+        if (ob < best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        if (on < nan_k) nan_k = on;
+    }
+    if (lane == 0) {
+        int32_t cell = (nan_k != 0x7fffffff) ? (int32_t)nan_k : (bk == 0x7fffffff ? 0 : (int32_t)bk);
+        cells[row] = cell;
+        if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
+    }
+}
+
+// standalone grid assignment (get_cells_indices on a grid tessellation) + optional offer
+template <int DD>
+__global__ void __launch_bounds__(256) qdx_cells_grid_kernel(const float* __restrict__ desc, int64_t B, const QdxGrid grid,
+                                                             const float* __restrict__ cent, int64_t K,
+                                                             int32_t* __restrict__ cells, void* ws, const float* rep_f,
+                                                             const float* __restrict__ fit, int32_t offer,
+                                                             uint32_t idx_base, int32_t first_wins) {
+    __shared__ float s_axes[QDX_MAX_AXES];
+    for (int i = threadIdx.x; i < grid.total_axes; i += blockDim.x) s_axes[i] = grid.axes[i];
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    float x[DD];
+#pragma unroll
+    for (int d = 0; d < DD; ++d) x[d] = desc[row * DD + d];
+    const int32_t cell = qdx_grid_cell<DD>(x, grid, s_axes, cent, K);
+    cells[row] = cell;
+    if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
+}
+
+// offer only: cells already known (tell / add with injected cells, or after an all-gather)
+__global__ void __launch_bounds__(256) qdx_offer_kernel(const int32_t* __restrict__ cells, const float* __restrict__ fit,
+                                                        int64_t B, int64_t K, void* ws, const float* rep_f,
+                                                        uint32_t idx_base, int32_t first_wins) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    const int32_t c = cells[row];
+    if (c < 0 || c >= K) { ((QdxWorkspace*)ws)->error = QDX_ERR_BAD_CELL; return; }
+    qdx_offer(qdx_ws_keytab(ws, K), rep_f, c, fit[row], idx_base + (uint32_t)row, first_wins);
+}
+
+// =====================================================================================================
+// commit: winners -> repertoire rows, reset the key table, QD metrics by the last CTA
+// =====================================================================================================
+__global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K, int32_t D, int32_t Dd,
+                                                         const float* __restrict__ off_g, const float* __restrict__ off_f,
+                                                         const float* __restrict__ off_d, uint32_t idx_base, int64_t B,
+                                                         int32_t first_wins, float* __restrict__ rep_g,
+                                                         float* __restrict__ rep_f, float* __restrict__ rep_d,
+                                                         float qd_offset, float* __restrict__ metrics_out,
+                                                         int32_t* __restrict__ added_cells, int32_t mode) {
+    // mode 0: commit winners whose offspring rows are in off_* (index = global idx - idx_base), reset keys, metrics
+    // mode 1: stage -- copy only the winners owned by [idx_base, idx_base + B) into rep_* (= staging rows by
+    //         cell), keep the key table, no metrics                       (multi-GPU winners-only exchange)
+    // mode 2: apply -- off_* are staging rows indexed by CELL; reset keys, metrics
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int added = 0;
+    for (int64_t c0 = warp_global * 32; c0 < K; c0 += nwarps * 32) {
+        // one coalesced 64-bit load per lane covers 32 cells; then the warp copies each changed row
+        const int64_t c = c0 + lane;
+        unsigned long long key = c < K ? keytab[c] : 0ull;
+        if (c < K && key != 0ull && mode != 1) keytab[c] = 0ull;
+        const bool win = key != 0ull && (uint32_t)(key >> 32) != 0xFFFFFFFFu;      // NaN-poisoned cells accept nobody
+        unsigned m = __ballot_sync(0xffffffffu, win);
+        added += __popc(m);
+        while (m) {
+            const int src = __ffs(m) - 1; m &= m - 1;
+            const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
+            const uint32_t lo = (uint32_t)k;
+            const int64_t cell = c0 + src;
+            int64_t i = (int64_t)(first_wins ? ~lo : lo) - (int64_t)idx_base;
+            if (mode == 2) i = cell;
+            else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) ws->error = QDX_ERR_BAD_INDEX; continue; }
+            const float* srow = off_g + i * D; float* drow = rep_g + cell * D;
+            if ((D & 3) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(srow); float4* d4 = reinterpret_cast<float4*>(drow);
+                for (int q = lane; q < (D >> 2); q += 32) d4[q] = __ldg(s4 + q);
+            } else {
+                for (int d = lane; d < D; d += 32) drow[d] = srow[d];
+            }
+            for (int d = lane; d < Dd; d += 32) rep_d[cell * Dd + d] = off_d[i * Dd + d];
+            if (lane == 0) { rep_f[cell] = off_f[i]; if (added_cells) added_cells[cell] = (int32_t)i; }
+        }
+    }
+    // ---- metrics by the last CTA to finish (deterministic fixed-shape reduction) -------------------------
+    __shared__ double s_sum[8]; __shared__ float s_max[8]; __shared__ int s_cnt[8]; __shared__ int s_nan[8]; __shared__ int s_add[8];
+    __shared__ bool s_last;
+    if (mode == 1) return;
+    if (lane == 0) s_add[threadIdx.x >> 5] = added;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0; for (int w = 0; w < (blockDim.x >> 5); ++w) a += s_add[w];
+        atomicAdd((int*)&ws->pad[0], a);
+        const unsigned t = atomicAdd(&ws->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double sum = 0.0; float mx = -INFINITY; int cnt = 0; int nan = 0;
+    for (int64_t c = threadIdx.x; c < K; c += blockDim.x) {
+        const float v = __ldcg(rep_f + c);
+        if (v != -INFINITY) { sum += (double)v; ++cnt; }
+        if (v != v) nan = 1; else if (v > mx) mx = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if (lane == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; s_cnt[threadIdx.x >> 5] = cnt; s_nan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; }
+        float out[4];
+        out[0] = (float)s + qd_offset * (float)n;                 // qd_score   (metrics.py:92-93)
+        out[1] = nn ? NAN : m;                                     // max_fitness (:95)
+        out[2] = 100.0f * __fdiv_rn((float)n, (float)K);           // coverage   (:94)
+        out[3] = (float)(int)(*(volatile uint32_t*)&ws->pad[0]);                           // offspring inserted by this call
+        for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (metrics_out) metrics_out[j] = out[j]; }
+        ws->ticket = 0u; ws->pad[0] = 0u;
+    }
+}
+
+// =====================================================================================================
+// small standalone ops of the preserved Python surface
+// =====================================================================================================
+// UniformSelector.select index stream (uniform_selector.py:48-55): key = key handed to select()
+__global__ void __launch_bounds__(256) qdx_select_kernel(void* ws_raw, QdxKey key, int64_t num, int32_t* __restrict__ out) {
+    __shared__ QdxSeg s_seg[QDX_MAX_SEG];
+    __shared__ float s_last[QDX_MAX_SEG];
+    const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
+    const int nseg = ws->sel.nseg;
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num) return;
+    if (nseg <= 0) { out[i] = 0; return; }     // empty repertoire: error flag raised by prepare; keep indices in range
+    const QdxKey sub = qdx_split(key, 1);
+    const float u = qdx_unit_float(qdx_bits32(sub, (uint64_t)i));
+    out[i] = qdx_ws_occ(ws_raw)[qdx_sel_rank(s_seg, s_last, nseg, ws->sel.total * (1.0f - u)) - 1];
+}
+
+// out[i, :] = src[idx[i], :]
+__global__ void __launch_bounds__(256) qdx_gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                              int64_t B, int32_t D, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= B) return;
+    const float* s = src + (int64_t)idx[row] * D; float* o = out + row * D;
+    if ((D & 3) == 0) {
+        for (int q = lane; q < (D >> 2); q += 32) reinterpret_cast<float4*>(o)[q] = __ldg(reinterpret_cast<const float4*>(s) + q);
+    } else {
+        for (int d = lane; d < D; d += 32) o[d] = s[d];
+    }
+}
+
+// isoline_variation(x1, x2, key) on dense parents (mutation_operators.py:175-226, one leaf)
+__global__ void __launch_bounds__(256) qdx_isoline_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          int64_t B, int32_t D, QdxKey key, float iso_sigma, float line_sigma,
+                                                          int32_t has_min, float minv, int32_t has_max, float maxv,
+                                                          float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * (int64_t)D) return;
+    const int64_t row = e / D;
+    const QdxKey k_line = qdx_split(key, 1);
+    const QdxKey k_leaf = qdx_split(qdx_split(key, 0), 0);
+    const float line = qdx_normal_from_bits(qdx_bits32(k_line, (uint64_t)row)) * line_sigma;
+    const float iso = qdx_normal_from_bits(qdx_bits32(k_leaf, (uint64_t)e)) * iso_sigma;
+    const float a = x1[e], b = x2[e];
+    float t1 = a + iso, t2 = b - a, t3 = t2 * line;
+    float x = t1 + t3;
+    if (has_min) x = qdx_max_nanprop(x, minv);
+    if (has_max) x = qdx_min_nanprop(x, maxv);
+    out[e] = x;
+}
+
+// jax.random.{bits, uniform, normal, split} streams for the host-facing qdax_b200.random module
+__global__ void __launch_bounds__(256) qdx_random_kernel(QdxKey key, int64_t n, int32_t kind, float minv, float maxv, void* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t bits = qdx_bits32(key, (uint64_t)i);
+    if (kind == 0) ((uint32_t*)out)[i] = bits;
+    else if (kind == 1) { float v = qdx_unit_float(bits) * (maxv - minv) + minv; ((float*)out)[i] = v < minv ? minv : v; }
+    else ((float*)out)[i] = qdx_normal_from_bits(bits);
+}
+
+// metrics only (default_qd_metrics on an arbitrary repertoire)
+__global__ void __launch_bounds__(256) qdx_metrics_kernel(const float* __restrict__ rep_f, int64_t K, float qd_offset, float* out) {
+    __shared__ double s_sum[8]; __shared__ float s_max[8]; __shared__ int s_cnt[8]; __shared__ int s_nan[8];
+    const int lane = threadIdx.x & 31;
+    double sum = 0.0; float mx = -INFINITY; int cnt = 0; int nan = 0;
+    for (int64_t c = threadIdx.x; c < K; c += blockDim.x) {
+        const float v = rep_f[c];
+        if (v != -INFINITY) { sum += (double)v; ++cnt; }
+        if (v != v) nan = 1; else if (v > mx) mx = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if (lane == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; s_cnt[threadIdx.x >> 5] = cnt; s_nan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; }
+        out[0] = (float)s + qd_offset * (float)n;
+        out[1] = nn ? NAN : m;
+        out[2] = 100.0f * __fdiv_rn((float)n, (float)K);
+    }
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
+    memset(g, 0, sizeof(*g));
+    if (!gd || gd->dd == 0) return 0;
+    if (gd->dd != desc_dim || gd->dd < 1 || gd->dd > QDX_MAX_GRID_DIM || !gd->axes) return QDX_ERR_ARG;
+    int off = 0;
+    for (int d = 0; d < gd->dd; ++d) {
+        if (gd->n[d] < 1) return QDX_ERR_ARG;
+        g->n[d] = gd->n[d]; g->stride[d] = gd->stride[d]; g->off[d] = off; g->lo[d] = gd->lo[d]; g->hi[d] = gd->hi[d];
+        off += gd->n[d];
+    }
+    if (off > QDX_MAX_AXES) return QDX_ERR_ARG;
+    g->dd = gd->dd; g->axes = gd->axes; g->total_axes = off;
+    return 0;
+}
+
+template <int TASK>
+static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, cudaStream_t st) {
+#define QDX_LAUNCH_GEN(GD)                                                                                         \
+    do {                                                                                                           \
+        cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<TASK, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                                       \
+        qdx_generate_kernel<TASK, GD><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);                                  \
+    } while (0)
+    const int gd = (TASK == QDX_TASK_NONE) ? 0 : p.grid.dd;
+    switch (gd) {
+        case 0: QDX_LAUNCH_GEN(0); break;
+        case 1: QDX_LAUNCH_GEN(1); break;
+        case 2: QDX_LAUNCH_GEN(2); break;
+        case 3: QDX_LAUNCH_GEN(3); break;
+        case 4: QDX_LAUNCH_GEN(4); break;
+        default: return QDX_ERR_ARG;
+    }
+#undef QDX_LAUNCH_GEN
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+
+extern "C" {
+
+int qdx_version(void) { return 100; }
+
+int qdx_workspace_bytes(int64_t K, int64_t* bytes) {
+    if (K <= 0 || K >= (1ll << 31) || !bytes) return QDX_ERR_ARG;
+    *bytes = (int64_t)qdx_ws_total_bytes(K);
+    return 0;
+}
+
+int qdx_workspace_keytab_offset(int64_t K, int64_t* offset) {
+    if (K <= 0 || K >= (1ll << 31) || !offset) return QDX_ERR_ARG;
+    *offset = (int64_t)qdx_ws_keytab_offset(K);
+    return 0;
+}
+
+int qdx_workspace_init(void* ws, int64_t K, void* stream) {
+    if (!ws || K <= 0) return QDX_ERR_ARG;
+    return (int)cudaMemsetAsync(ws, 0, qdx_ws_total_bytes(K), S(stream));
+}
+
+int qdx_workspace_set_carry_key(void* ws, uint32_t k0, uint32_t k1, void* stream) {
+    if (!ws) return QDX_ERR_ARG;
+    uint32_t k[2] = {k0, k1};
+    // 8-byte async copy from pageable memory is staged by the runtime before returning
+    return (int)cudaMemcpyAsync((char*)ws + offsetof(QdxWorkspace, carry), k, sizeof(k), cudaMemcpyHostToDevice, S(stream));
+}
+
+int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream) {
+    if (!ws) return QDX_ERR_ARG;
+    QdxWorkspace h;   // header only (a few KB)
+    cudaError_t e = cudaMemcpyAsync(&h, ws, sizeof(QdxWorkspace), cudaMemcpyDeviceToHost, S(stream));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(S(stream));
+    if (e != cudaSuccess) return (int)e;
+    if (carry_key2) { carry_key2[0] = h.carry.a; carry_key2[1] = h.carry.b; }
+    if (metrics4) for (int j = 0; j < 4; ++j) metrics4[j] = h.metrics[j];
+    if (error) *error = h.error;
+    return 0;
+}
+
+int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t key_mode, uint32_t k0, uint32_t k1, void* stream) {
+    if (!rep_fitness || !ws || K <= 0 || key_mode < 0 || key_mode > 4) return QDX_ERR_ARG;
+    qdx_prepare_kernel<<<1, 1024, 0, S(stream)>>>(rep_fitness, K, ws, QdxKey{k0, k1}, key_mode);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
+                 int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
+                 float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
+                 uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, void* stream) {
+    if (!rep_genotypes || !rep_fitness || !ws || K <= 0 || D <= 0 || B < 0 || (D & 3)) return QDX_ERR_ARG;
+    if (task < QDX_TASK_NONE || task > QDX_TASK_SPHERE) return QDX_ERR_ARG;
+    if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
+    if (task == QDX_TASK_ARM && desc_dim != 2) return QDX_ERR_ARG;
+    if (task == QDX_TASK_NONE && (!out_genotypes || offer)) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    QdxGenParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_grid(task == QDX_TASK_NONE ? nullptr : grid, desc_dim, &p.grid);
+    if (rc) return rc;
+    if (offer && p.grid.dd == 0) return QDX_ERR_ARG;          // offer needs cells: grid fast path only
+    if (p.grid.dd && !centroids) return QDX_ERR_ARG;
+    p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.centroids = centroids; p.ws = ws;
+    p.B = B; p.K = K; p.D = (int32_t)D;
+    // chunk of genes staged per warp tile: whole row when it fits 16 KB per warp, else 128 genes
+    p.DC = (D <= 128) ? (int32_t)D : 128;
+    p.DS = ((p.DC & 7) == 4) ? p.DC : p.DC + 4;
+    if (task == QDX_TASK_ARM && D > p.DC) return QDX_ERR_UNSUPPORTED;   // arm needs the whole row for its two passes
+    p.iso_sigma = iso_sigma; p.line_sigma = line_sigma; p.has_min = has_min; p.has_max = has_max; p.minv = minval; p.maxv = maxval;
+    p.out_g = out_genotypes; p.out_f = out_fitness; p.out_d = out_desc; p.out_cell = out_cells; p.out_p1 = out_p1; p.out_p2 = out_p2;
+    p.desc_dim = desc_dim; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
+    const size_t smem = (size_t)QDX_GEN_WARPS * 32 * p.DS * sizeof(float);
+    const dim3 g((unsigned)((B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32)));
+    switch (task) {
+        case QDX_TASK_NONE: return launch_generate_task<QDX_TASK_NONE>(p, smem, g, S(stream));
+        case QDX_TASK_ARM: return launch_generate_task<QDX_TASK_ARM>(p, smem, g, S(stream));
+        case QDX_TASK_RASTRIGIN: return launch_generate_task<QDX_TASK_RASTRIGIN>(p, smem, g, S(stream));
+        default: return launch_generate_task<QDX_TASK_SPHERE>(p, smem, g, S(stream));
+    }
+}
+
+int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
+              float* out_desc, void* stream) {
+    if (!genotypes || !out_fitness || !out_desc || B < 0 || D <= 0 || desc_dim < 1 || desc_dim > D) return QDX_ERR_ARG;
+    if (task < QDX_TASK_ARM || task > QDX_TASK_SPHERE || (task == QDX_TASK_ARM && desc_dim != 2)) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    const size_t smem = 4 * 32 * (64 + 1) * sizeof(float);
+    const dim3 g((unsigned)((B + 127) / 128));
+    if (task == QDX_TASK_ARM) qdx_score_kernel<QDX_TASK_ARM><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
+    else if (task == QDX_TASK_RASTRIGIN) qdx_score_kernel<QDX_TASK_RASTRIGIN><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
+    else qdx_score_kernel<QDX_TASK_SPHERE><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const qdx_grid_desc* grid,
+              int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
+              uint32_t idx_base, int32_t first_wins, void* stream) {
+    if (!desc || !centroids || !out_cells || B < 0 || K <= 0 || desc_dim < 1) return QDX_ERR_ARG;
+    if (offer && (!ws || !rep_fitness || !fitness)) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    QdxGrid g;
+    int rc = fill_grid(grid, desc_dim, &g);
+    if (rc) return rc;
+    cudaStream_t st = S(stream);
+    if (g.dd) {
+        const dim3 gr((unsigned)((B + 255) / 256));
+        switch (g.dd) {
+            case 1: qdx_cells_grid_kernel<1><<<gr, 256, 0, st>>>(desc, B, g, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            case 2: qdx_cells_grid_kernel<2><<<gr, 256, 0, st>>>(desc, B, g, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            case 3: qdx_cells_grid_kernel<3><<<gr, 256, 0, st>>>(desc, B, g, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            default: qdx_cells_grid_kernel<4><<<gr, 256, 0, st>>>(desc, B, g, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+        }
+    } else if (desc_dim <= 4) {
+        const dim3 gr((unsigned)((B + 255) / 256));
+        const size_t smem = (size_t)2048 * desc_dim * sizeof(float);
+        switch (desc_dim) {
+            case 1: qdx_cells_bf_kernel<1><<<gr, 256, smem, st>>>(desc, B, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            case 2: qdx_cells_bf_kernel<2><<<gr, 256, smem, st>>>(desc, B, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            case 3: qdx_cells_bf_kernel<3><<<gr, 256, smem, st>>>(desc, B, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+            default: qdx_cells_bf_kernel<4><<<gr, 256, smem, st>>>(desc, B, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins); break;
+        }
+    } else {
+        const dim3 gr((unsigned)((B * 32 + 127) / 128));
+        qdx_cells_bf_generic_kernel<<<gr, 128, 0, st>>>(desc, B, desc_dim, centroids, K, out_cells, ws, rep_fitness, fitness, offer, idx_base, first_wins);
+    }
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_offer_cells(const int32_t* cells, const float* fitness, int64_t B, int64_t K, void* ws, const float* rep_fitness,
+                    uint32_t idx_base, int32_t first_wins, void* stream) {
+    if (!cells || !fitness || !ws || !rep_fitness || B < 0 || K <= 0) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    qdx_offer_kernel<<<(unsigned)((B + 255) / 256), 256, 0, S(stream)>>>(cells, fitness, B, K, ws, rep_fitness, idx_base, first_wins);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
+               const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
+               float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
+               int32_t mode, void* stream) {
+    if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
+    if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
+    int64_t warps = (K + 31) / 32;
+    int64_t ctas = (warps + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    if (ctas < 1) ctas = 1;
+    qdx_commit_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
+                                                            idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
+                                                            qd_offset, metrics_out4, added_cells, mode);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_select_indices(void* ws, uint32_t k0, uint32_t k1, int64_t num, int32_t* out, void* stream) {
+    if (!ws || !out || num < 0) return QDX_ERR_ARG;
+    if (num == 0) return 0;
+    qdx_select_kernel<<<(unsigned)((num + 255) / 256), 256, 0, S(stream)>>>(ws, QdxKey{k0, k1}, num, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, float* out, void* stream) {
+    if (!src || !idx || !out || B < 0 || D <= 0) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    qdx_gather_rows_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, S(stream)>>>(src, idx, B, (int32_t)D, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,
+                          float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval, float* out,
+                          void* stream) {
+    if (!x1 || !x2 || !out || B < 0 || D <= 0) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    const int64_t n = B * D;
+    qdx_isoline_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(x1, x2, B, (int32_t)D, QdxKey{k0, k1}, iso_sigma, line_sigma,
+                                                                         has_min, minval, has_max, maxval, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_random(uint32_t k0, uint32_t k1, int64_t n, int32_t kind, float minval, float maxval, void* out, void* stream) {
+    if (!out || n < 0 || kind < 0 || kind > 2) return QDX_ERR_ARG;
+    if (n == 0) return 0;
+    qdx_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(QdxKey{k0, k1}, n, kind, minval, maxval, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_metrics(const float* rep_fitness, int64_t K, float qd_offset, float* out3, void* stream) {
+    if (!rep_fitness || !out3 || K <= 0) return QDX_ERR_ARG;
+    qdx_metrics_kernel<<<1, 256, 0, S(stream)>>>(rep_fitness, K, qd_offset, out3);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+// host-only helper (no GPU): expands the selection segments to T[1..M] for tests of the closed form
+int qdx_host_select_table(int32_t M, float* out_T, int32_t* out_nseg) {
+    if (M <= 0 || !out_T) return QDX_ERR_ARG;
+    QdxSel sel;
+    qdx_build_sel(M, &sel);
+    if (sel.nseg <= 0) return QDX_ERR_UNSUPPORTED;
+    for (int s = 0; s < sel.nseg; ++s)
+        for (int i = 0; i <= sel.seg[s].n; ++i) out_T[sel.seg[s].j0 + i - 1] = qdx_seg_value(sel.seg[s], i);
+    if (out_nseg) *out_nseg = sel.nseg;
+    return 0;
+}
+
+// host-only helper: rank lookup through the segments (tests)
+int qdx_host_select_rank(int32_t M, const float* r, int64_t n, int32_t* out_rank) {
+    if (M <= 0 || !r || !out_rank) return QDX_ERR_ARG;
+    QdxSel sel;
+    qdx_build_sel(M, &sel);
+    if (sel.nseg <= 0) return QDX_ERR_UNSUPPORTED;
+    for (int64_t i = 0; i < n; ++i) out_rank[i] = qdx_sel_rank(sel.seg, sel.last, sel.nseg, r[i]);
+    return 0;
+}
+
+}  // extern "C"

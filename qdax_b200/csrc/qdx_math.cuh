@@ -1,0 +1,151 @@
+// QDX-F32 arithmetic on the device: Threefry-2x32-20 (JAX partitionable mode), the uniform / normal
+// bit tricks of jax.random, and the log1p / erfinv / sincos kernels -- every rounding step explicit.
+// This translation unit family is compiled with -fmad=false, so a*b+c is two roundings unless
+// __fmaf_rn is written.  The same operation sequence is restated (independently, in C) by
+// oracle/qdx_oracle.c; tests compare the two bit for bit.
+//
+// Reference call sites (under /root/reference): jax.random.split/uniform/normal/choice in
+// qdax/core/emitters/mutation_operators.py:205-220, repertoire_selectors/uniform_selector.py:48-55,
+// qdax/core/map_elites.py:177-241; jnp.cos/sin/cumsum in qdax/tasks/arm.py:28-36 and
+// qdax/tasks/standard_functions.py:13-15.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define QDX_DEV __device__ __forceinline__
+
+struct QdxKey { uint32_t a, b; };
+
+QDX_DEV uint32_t qdx_rotl(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+// Threefry-2x32, 20 rounds; key schedule ks = (k0, k1, k0^k1^0x1BD11BDA).
+QDX_DEV void qdx_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+    const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+    uint32_t x0 = c0 + k0, x1 = c1 + k1;
+#define QDX_R(r) x0 += x1; x1 = qdx_rotl(x1, r); x1 ^= x0;
+    QDX_R(13) QDX_R(15) QDX_R(26) QDX_R(6)
+    x0 += k1; x1 += k2 + 1u;
+    QDX_R(17) QDX_R(29) QDX_R(16) QDX_R(24)
+    x0 += k2; x1 += k0 + 2u;
+    QDX_R(13) QDX_R(15) QDX_R(26) QDX_R(6)
+    x0 += k0; x1 += k1 + 3u;
+    QDX_R(17) QDX_R(29) QDX_R(16) QDX_R(24)
+    x0 += k1; x1 += k2 + 4u;
+    QDX_R(13) QDX_R(15) QDX_R(26) QDX_R(6)
+    x0 += k2; x1 += k0 + 5u;
+#undef QDX_R
+    o0 = x0; o1 = x1;
+}
+
+// jax.random.split(key, n)[i]
+QDX_DEV QdxKey qdx_split(QdxKey k, uint64_t i) {
+    QdxKey o;
+    qdx_threefry2x32(k.a, k.b, (uint32_t)(i >> 32), (uint32_t)i, o.a, o.b);
+    return o;
+}
+// random_bits(key, 32, shape)[flat i]
+QDX_DEV uint32_t qdx_bits32(QdxKey k, uint64_t i) {
+    uint32_t a, b;
+    qdx_threefry2x32(k.a, k.b, (uint32_t)(i >> 32), (uint32_t)i, a, b);
+    return a ^ b;
+}
+QDX_DEV float qdx_unit_float(uint32_t bits) { return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
+
+// jnp.maximum / jnp.minimum as compares: NaN propagates like XLA max/min.
+QDX_DEV float qdx_max_nanprop(float x, float lo) { return x < lo ? lo : x; }
+QDX_DEV float qdx_min_nanprop(float x, float hi) { return x > hi ? hi : x; }
+
+// log(t), t > 0 normal: t = m * 2^e, m in [sqrt(1/2), sqrt(2)).
+QDX_DEV float qdx_logf(float t) {
+    uint32_t ix = __float_as_uint(t) - 0x3f3504f3u;
+    int e = (int32_t)ix >> 23;
+    float m = __uint_as_float((ix & 0x007fffffu) + 0x3f3504f3u);
+    float r = m - 1.0f;
+    float z = r * r;
+    float p = 7.0376836292E-2f;
+    p = __fmaf_rn(p, r, -1.1514610310E-1f);
+    p = __fmaf_rn(p, r, 1.1676998740E-1f);
+    p = __fmaf_rn(p, r, -1.2420140846E-1f);
+    p = __fmaf_rn(p, r, 1.4249322787E-1f);
+    p = __fmaf_rn(p, r, -1.6668057665E-1f);
+    p = __fmaf_rn(p, r, 2.0000714765E-1f);
+    p = __fmaf_rn(p, r, -2.4999993993E-1f);
+    p = __fmaf_rn(p, r, 3.3333331174E-1f);
+    float y = (p * r) * z;
+    float fe = (float)e;
+    y = __fmaf_rn(fe, -2.12194440e-4f, y);
+    y = __fmaf_rn(z, -0.5f, y);
+    float res = r + y;
+    res = __fmaf_rn(fe, 0.693359375f, res);
+    return res;
+}
+// log1p(y), y in (-1, 0]
+QDX_DEV float qdx_log1pf(float y) {
+    float t = 1.0f + y;
+    if (t == 1.0f) return y;
+    float c = __fdiv_rn(y - (t - 1.0f), t);
+    return qdx_logf(t) + c;
+}
+// XLA ErfInv32 (Giles), fused Horner.
+QDX_DEV float qdx_erfinvf(float x) {
+    float w = -qdx_log1pf(-(x * x));
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f;
+        p = __fmaf_rn(p, w, 3.43273939e-07f);
+        p = __fmaf_rn(p, w, -3.5233877e-06f);
+        p = __fmaf_rn(p, w, -4.39150654e-06f);
+        p = __fmaf_rn(p, w, 0.00021858087f);
+        p = __fmaf_rn(p, w, -0.00125372503f);
+        p = __fmaf_rn(p, w, -0.00417768164f);
+        p = __fmaf_rn(p, w, 0.246640727f);
+        p = __fmaf_rn(p, w, 1.50140941f);
+    } else {
+        w = __fsqrt_rn(w) - 3.0f;
+        p = -0.000200214257f;
+        p = __fmaf_rn(p, w, 0.000100950558f);
+        p = __fmaf_rn(p, w, 0.00134934322f);
+        p = __fmaf_rn(p, w, -0.00367342844f);
+        p = __fmaf_rn(p, w, 0.00573950773f);
+        p = __fmaf_rn(p, w, -0.0076224613f);
+        p = __fmaf_rn(p, w, 0.00943887047f);
+        p = __fmaf_rn(p, w, 1.00167406f);
+        p = __fmaf_rn(p, w, 2.83297682f);
+    }
+    if (fabsf(x) == 1.0f) return x * 3.40282347e+38f;
+    return p * x;
+}
+// jax.random.normal from one 32-bit draw.
+QDX_DEV float qdx_normal_from_bits(uint32_t bits) {
+    const float lo = -0x1.fffffep-1f;
+    float f = qdx_unit_float(bits);
+    float u = f * 2.0f + lo;
+    u = u < lo ? lo : u;
+    return 0x1.6a09e6p+0f * qdx_erfinvf(u);
+}
+// sin & cos: 3-term Cody-Waite by pi/2 (fused), minimax kernels on [-pi/4, pi/4].
+QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
+    float q = rintf(th * 0x1.45f306p-1f);
+    float r = __fmaf_rn(q, -0x1.921fb6p+0f, th);
+    r = __fmaf_rn(q, 0x1.777a5cp-25f, r);
+    r = __fmaf_rn(q, 0x1.ee59dap-50f, r);
+    int n = (int)q & 3;
+    float s = r * r;
+    float ps = __fmaf_rn(__fmaf_rn(-1.9515295891E-4f, s, 8.3321608736E-3f), s, -1.6666654611E-1f);
+    float sr = __fmaf_rn(r * s, ps, r);
+    float pc = __fmaf_rn(__fmaf_rn(2.443315711809948E-5f, s, -1.388731625493765E-3f), s, 4.166664568298827E-2f);
+    float cr = __fmaf_rn(s * s, pc, __fmaf_rn(s, -0.5f, 1.0f));
+    float sv = (n & 1) ? cr : sr;
+    float cv = (n & 1) ? sr : cr;
+    if (n & 2) sv = -sv;
+    if ((n + 1) & 2) cv = -cv;
+    s_out = sv; c_out = cv;
+}
+
+// Total order key for a fitness: -inf < ... < -0 == +0 < ... < +inf < NaN (NaN = 0xFFFFFFFF).
+QDX_DEV uint32_t qdx_order_key(float v) {
+    if (v != v) return 0xFFFFFFFFu;
+    uint32_t u = __float_as_uint(v == 0.0f ? 0.0f : v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}

@@ -1,0 +1,487 @@
+"""GPU parity tests: hand-written CUDA path (through the C ABI, via qdax_b200) vs the oracle on the same
+seeded inputs.  Integer / index / decision results must be bit-exact; floating-point results are required to be
+bit-exact too against the exact-arithmetic C oracle (QDX-F32 spec) and within 1e-5 relative of the literal
+NumPy restatement (the tolerance BASELINE.json's north_star states)."""
+import functools
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import jax_prng as jr  # noqa: E402
+from oracle import qdax_numpy as qn  # noqa: E402
+
+RTOL = 1e-5  # north_star tolerance for genotypes / fitnesses / QD-score
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def T(a, dev, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------- PRNG
+def test_random_streams_bit_exact(dev, co):
+    from qdax_b200 import random as qr
+
+    for seed, n in [(0, 8), (42, 1), (7, 4097), (2026, 100003)]:
+        k = jr.key(seed)
+        assert np.array_equal(N(qr.bits(k, (n,), device=dev)).view(np.uint32), co.random_bits(k, n))
+        assert np.array_equal(N(qr.uniform(k, (n,), device=dev)), co.uniform(k, n))
+        assert np.array_equal(N(qr.uniform(k, (n,), minval=-2.0, maxval=3.0, device=dev)), co.uniform(k, n, -2.0, 3.0))
+        assert np.array_equal(N(qr.normal(k, (n,), device=dev)), co.normal(k, n))
+    assert (qr.split(jr.key(0)) == jr.split(jr.key(0))).all() and (qr.split(jr.key(9), 5) == jr.split(jr.key(9), 5)).all()
+    assert float(qr.normal(jr.key(42), (1,), device=dev)[0]) == pytest.approx(-0.028304616, abs=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------- selection
+@pytest.mark.parametrize("K,occ", [(1, 1.0), (7, 0.5), (256, 0.5), (10000, 0.01), (10000, 0.37), (10000, 1.0), (50000, 0.9)])
+def test_uniform_selector_indices(dev, co, K, occ):
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+    from qdax_b200.core.emitters.repertoire_selectors.uniform_selector import UniformSelector
+
+    rng = np.random.default_rng(K)
+    fit = np.where(rng.random(K) < occ, rng.standard_normal(K), -np.inf).astype(np.float32)
+    if not np.isfinite(fit).any():
+        fit[K // 2] = 0.0
+    rep = MapElitesRepertoire(T(rng.random((K, 8)), dev), T(fit.reshape(-1, 1), dev), T(np.zeros((K, 2)), dev), T(rng.random((K, 2)), dev))
+    for seed in (1, 2):
+        key = jr.key(seed)
+        idx = N(UniformSelector().select_indices(rep, key, 5000))
+        assert np.array_equal(idx, co.select_indices(fit, key, 5000))
+    sel = rep.select(jr.key(3), 64)
+    ref = co.select_indices(fit, jr.key(3), 64)
+    assert np.array_equal(N(sel.genotypes), N(rep.genotypes)[ref]) and np.array_equal(N(sel.fitnesses), fit[ref].reshape(-1, 1))
+
+
+def test_select_from_empty_repertoire_raises(dev):
+    from qdax_b200._lib import QdxError
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+
+    K = 16
+    rep = MapElitesRepertoire(torch.zeros(K, 4, device=dev), torch.full((K, 1), -np.inf, device=dev), torch.zeros(K, 2, device=dev),
+                              torch.rand(K, 2, device=dev))
+    rep.select(jr.key(0), 4)
+    with pytest.raises(QdxError):
+        rep._workspace().check()
+
+
+# ------------------------------------------------------------------------------------------------- variation
+@pytest.mark.parametrize("B,D", [(1, 4), (33, 20), (1000, 100), (257, 7)])
+def test_isoline_variation_dense(dev, co, B, D):
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+
+    rng = np.random.default_rng(B * D)
+    x1, x2 = rng.random((B, D)).astype(np.float32), rng.random((B, D)).astype(np.float32)
+    for clip in [(0.0, 1.0), (None, None), (0.2, None)]:
+        got = N(isoline_variation(T(x1, dev), T(x2, dev), jr.key(5), 0.05, 0.1, clip[0], clip[1]))
+        assert np.array_equal(got, co.isoline_variation(x1, x2, jr.key(5), 0.05, 0.1, clip[0], clip[1]))
+        ref = qn.isoline_variation(x1, x2, jr.key(5), 0.05, 0.1, clip[0], clip[1])
+        assert np.allclose(got, ref, rtol=RTOL, atol=1e-6)
+
+
+def _make_rep(dev, K, D, occ, seed, centroids):
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+
+    rng = np.random.default_rng(seed)
+    fit = np.where(rng.random(K) < occ, rng.standard_normal(K), -np.inf).astype(np.float32)
+    fit[0] = 0.5
+    g = np.where(np.isinf(fit)[:, None], 0, rng.random((K, D))).astype(np.float32)
+    d = np.where(np.isinf(fit)[:, None], 0, centroids).astype(np.float32)
+    rep = MapElitesRepertoire(T(g, dev), T(fit.reshape(-1, 1), dev), T(d, dev), T(centroids, dev))
+    return rep, g, fit, d
+
+
+@pytest.mark.parametrize("B,D,K", [(64, 20, 256), (1000, 100, 400), (31, 8, 16), (4099, 100, 10000), (96, 256, 64)])
+def test_mixing_emitter_fused_emit(dev, co, B, D, K):
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+
+    n = int(round(np.sqrt(K)))
+    cent = qn.compute_euclidean_centroids((n, K // n), 0.0, 1.0)
+    rep, g, fit, _ = _make_rep(dev, K, D, 0.4, B + D, cent)
+    em = MixingEmitter(lambda x, k: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B)
+    x, extra = em.emit(rep, None, jr.key(11))
+    ref, p1, p2 = co.emit_isoline(g, fit, jr.key(11), B, 0.05, 0.1, 0.0, 1.0)
+    assert extra == {} and np.array_equal(N(x), ref)
+    # generic path (selector given explicitly is still uniform; a python variation_fn forces select+gather+kernel)
+    em2 = MixingEmitter(lambda x, k: x, lambda a, b, k: isoline_variation(a, b, k, 0.05, 0.1, 0.0, 1.0), 1.0, B)
+    x2, _ = em2.emit(rep, None, jr.key(11))
+    assert np.array_equal(N(x2), ref)
+
+
+# ------------------------------------------------------------------------------------------------- scoring
+@pytest.mark.parametrize("task", ["arm", "rastrigin", "sphere"])
+@pytest.mark.parametrize("B,D", [(1, 2), (7, 4), (33, 100), (1000, 100), (130, 1000), (65, 33)])
+def test_scoring_functions(dev, co, task, B, D):
+    from qdax_b200.tasks.arm import arm_scoring_function
+    from qdax_b200.tasks.standard_functions import rastrigin_scoring_function, sphere_scoring_function
+
+    fn = {"arm": arm_scoring_function, "rastrigin": rastrigin_scoring_function, "sphere": sphere_scoring_function}[task]
+    rng = np.random.default_rng(D)
+    g = (rng.random((B, D)) * 1.2 - 0.1).astype(np.float32)
+    f, d, extra = fn(T(g, dev), jr.key(0))
+    fo, do = co.score(task, g)
+    assert extra == {} and np.array_equal(N(f), fo) and np.array_equal(N(d), do)
+    fn_, dn_ = qn.SCORING[task](g)
+    assert np.allclose(N(f), fn_, rtol=RTOL, atol=1e-6) and np.allclose(N(d), dn_, rtol=RTOL, atol=1e-6)
+
+
+def test_arm_reference_kat(dev):
+    # /root/reference/tests/tasks_test/arm_test.py:123-163
+    from qdax_b200.tasks.arm import arm_scoring_function
+
+    cases = [(np.ones((1, 4)) * 0.5, [1.0, 0.5]), (np.zeros((1, 6)), [0.5, 0.5]), (np.ones((1, 10)), [0.5, 0.5]),
+             (np.array([[0, 0.5]]), [0.0, 0.5]), (np.array([[0.25, 0.5]]), [0.5, 0.0]), (np.array([[0.5, 0.5]]), [1.0, 0.5]),
+             (np.array([[0.75, 0.5]]), [0.5, 1.0])]
+    for g, exp in cases:
+        _, d, _ = arm_scoring_function(T(g, dev), jr.key(42))
+        assert np.array_equal(np.around(N(d), 1) + 0.0, np.array([exp], np.float32))
+
+
+# ------------------------------------------------------------------------------------------------- cells
+def _adversarial_descriptors(rng, cent, axes_list, n_rand):
+    Dd = cent.shape[1]
+    pts = [rng.random((n_rand, Dd)).astype(np.float32) * 1.4 - 0.2]
+    pts.append(cent[rng.integers(0, len(cent), 256)])                                   # exactly on centroids
+    mids = [((a[:-1].astype(np.float64) + a[1:]) / 2).astype(np.float32) for a in axes_list]
+    bis = np.stack([m[rng.integers(0, len(m), 512)] if len(m) else np.zeros(512, np.float32) for m in mids], axis=-1)
+    pts.append(bis)                                                                     # on bisectors (ties)
+    pts.append(np.nextafter(bis, np.float32(2)).astype(np.float32))
+    pts.append(np.nextafter(bis, np.float32(-2)).astype(np.float32))
+    far = rng.standard_normal((64, Dd)).astype(np.float32) * 50
+    pts.append(far)                                                                     # far outside -> brute force fallback
+    sp = np.zeros((6, Dd), np.float32)
+    sp[0, 0], sp[1, 0], sp[2, 0], sp[3, -1], sp[4, :], sp[5, :] = np.nan, np.inf, -np.inf, np.nan, 1e30, -1e-30
+    pts.append(sp)
+    return np.concatenate(pts).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (100, 100), (16, 3), (1, 5), (7,), (4, 5, 6), (3, 4, 2, 5)])
+def test_cells_grid_equals_bruteforce(dev, co, shape):
+    from qdax_b200 import _native
+    from qdax_b200.core.containers.mapelites_repertoire import compute_euclidean_centroids, get_cells_indices
+
+    cent_t = compute_euclidean_centroids(shape, 0.0, 1.0, device=dev)
+    cent = N(cent_t)
+    assert np.array_equal(cent, qn.compute_euclidean_centroids(shape, 0.0, 1.0))
+    grid = _native.grid_of(cent_t)
+    assert grid is not None and sorted(grid.n) == sorted(shape)
+    rng = np.random.default_rng(len(shape) * 100 + shape[0])
+    axes = [np.unique(cent[:, d]) for d in range(cent.shape[1])]
+    desc = _adversarial_descriptors(rng, cent, axes, 20000)
+    got = N(get_cells_indices(T(desc, dev), cent_t))
+    assert np.array_equal(got, co.cells(desc, cent))
+    # the brute-force kernel on the same inputs (grid detection bypassed)
+    got_bf = N(_native.cells(T(desc, dev), cent_t, None))
+    assert np.array_equal(got_bf, got)
+
+
+def test_cells_reference_tie_cases(dev):
+    from qdax_b200.core.containers.mapelites_repertoire import compute_euclidean_centroids, get_cells_indices
+
+    cent = compute_euclidean_centroids((2, 2), 0.0, 1.0, device=dev)
+    d = T(np.array([[0.5, 0.5], [0.1, 0.1], [0.9, 0.9], [0.5, 0.1], [np.nan, 0.3]], np.float32), dev)
+    assert N(get_cells_indices(d, cent)).tolist() == [0, 0, 3, 0, 0]
+
+
+@pytest.mark.parametrize("K,Dd,B", [(10000, 2, 20000), (1000, 3, 5000), (257, 1, 1000), (5000, 4, 3000), (300, 8, 1000), (2000, 32, 2048)])
+def test_cells_bruteforce_cvt(dev, co, K, Dd, B):
+    from qdax_b200.core.containers.mapelites_repertoire import get_cells_indices
+
+    rng = np.random.default_rng(K + Dd)
+    cent = rng.random((K, Dd)).astype(np.float32)
+    cent[K // 3] = cent[K // 5]  # duplicated centroid: first index must win
+    desc = rng.random((B, Dd)).astype(np.float32)
+    desc[:16] = cent[K // 3]
+    desc[16, 0] = np.nan
+    desc[17, Dd - 1] = np.inf
+    got = N(get_cells_indices(T(desc, dev), T(cent, dev)))
+    assert np.array_equal(got, co.cells(desc, cent))
+    assert np.array_equal(got[:4096], qn.get_cells_indices(desc[:4096], cent))
+
+
+# ------------------------------------------------------------------------------------------------- insertion
+def test_reference_add_kat(dev):
+    # /root/reference/tests/core_test/containers_test/mapelites_repertoire_test.py:11-81
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire, compute_euclidean_centroids
+
+    cent = compute_euclidean_centroids((2, 2), 0.0, 1.0, device=dev)
+    assert np.allclose(N(cent), [[0.25, 0.25], [0.75, 0.25], [0.25, 0.75], [0.75, 0.75]], atol=1e-6)
+    rep = MapElitesRepertoire.init(genotypes=torch.zeros(4, 12, device=dev), fitnesses=torch.full((4,), -np.inf, device=dev),
+                                   descriptors=torch.zeros(4, 2, device=dev), centroids=cent)
+    assert (N(rep.fitnesses) == -np.inf).all()
+    rep2 = rep.add(torch.ones(2, 12, device=dev), T(np.array([[0.1, 0.1], [0.9, 0.9]]), dev), torch.zeros(2, device=dev), {})
+    exp_g = np.array([[1.0] * 12, [0.0] * 12, [0.0] * 12, [1.0] * 12])
+    assert np.allclose(N(rep2.genotypes), exp_g, atol=1e-6)
+    assert np.array_equal(N(rep2.fitnesses).ravel(), np.array([0.0, -np.inf, -np.inf, 0.0], np.float32))
+    assert np.allclose(N(rep2.descriptors), [[0.1, 0.1], [0, 0], [0, 0], [0.9, 0.9]], atol=1e-6)
+    assert (N(rep.fitnesses) == -np.inf).all()  # value semantics: the input repertoire is untouched
+
+
+@pytest.mark.parametrize("tb", ["first", "last"])
+def test_add_golden_injected(dev, golden, tb):
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+
+    g = golden
+    rep = MapElitesRepertoire(T(g["S_rep_g"], dev), T(g["S_rep_f"].reshape(-1, 1), dev), T(g["S_rep_d"], dev), T(g["S_centroids"], dev), tie_break=tb)
+    new = rep.add(T(g["S_emit_x"], dev), T(g["S_inj_d"], dev), T(g["S_inj_f"], dev))
+    assert np.array_equal(N(new.genotypes), g[f"S_add_{tb}_g"])
+    assert np.array_equal(N(new.fitnesses).ravel(), g[f"S_add_{tb}_f"], equal_nan=True)
+    assert np.array_equal(N(new.descriptors), g[f"S_add_{tb}_d"])
+
+
+@pytest.mark.parametrize("B,K,D,levels", [(50000, 10000, 100, 5), (100, 10000, 100, 1000), (65536, 100, 8, 3), (1, 4, 4, 1), (4096, 2500, 12, 2)])
+@pytest.mark.parametrize("tb", ["first", "last"])
+def test_add_injected_random(dev, co, B, K, D, levels, tb):
+    """Injected identical offspring: cells, insertion decisions and the resulting repertoire are bit-exact,
+    including heavy same-cell equal-fitness ties, NaN (poisons the cell), -inf, +inf and -0.0 / +0.0."""
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire, get_cells_indices
+
+    rng = np.random.default_rng(B + K + levels)
+    n = int(round(np.sqrt(K)))
+    cent = qn.compute_euclidean_centroids((n, K // n), 0.0, 1.0)
+    rep, g0, f0, d0 = _make_rep(dev, K, D, 0.5, B, cent)
+    rep.tie_break = tb
+    g = rng.random((B, D)).astype(np.float32)
+    f = (rng.integers(0, levels, B) / max(levels - 1, 1) - 0.3).astype(np.float32)
+    if B >= 100:
+        f[rng.integers(0, B, 8)] = np.nan
+        f[rng.integers(0, B, 8)] = -np.inf
+        f[rng.integers(0, B, 4)] = np.inf
+        f[rng.integers(0, B, 8)] = -0.0
+        f[rng.integers(0, B, 8)] = 0.0
+    d = (rng.random((B, 2)) * 1.1 - 0.05).astype(np.float32)
+    new = rep.add(T(g, dev), T(d, dev), T(f, dev))
+    cells = co.cells(d, cent)
+    assert np.array_equal(N(get_cells_indices(T(d, dev), rep.centroids)), cells)
+    G, F, Dn, _ = co.add(g0, f0, d0, g, f, d, cells, tb)
+    assert np.array_equal(N(new.genotypes), G)
+    assert np.array_equal(N(new.fitnesses).ravel().view(np.uint32), F.view(np.uint32))   # bit pattern: -0.0 vs +0.0 too
+    assert np.array_equal(N(new.descriptors), Dn)
+    # idempotence: re-adding the repertoire's own contents changes nothing
+    occ = np.isfinite(F) | (F == np.inf)
+    again = new.add(T(G[occ], dev), T(Dn[occ], dev), T(F[occ], dev))
+    assert np.array_equal(N(again.genotypes), G) and np.array_equal(N(again.fitnesses).ravel().view(np.uint32), F.view(np.uint32))
+    # order invariance except through the declared tie-break: strictly distinct fitnesses -> permutation-proof
+    fu = rng.permutation(B).astype(np.float32)
+    perm = rng.permutation(B)
+    a = rep.add(T(g, dev), T(d, dev), T(fu, dev))
+    b = rep.add(T(g[perm], dev), T(d[perm], dev), T(fu[perm], dev))
+    assert np.array_equal(N(a.genotypes), N(b.genotypes)) and np.array_equal(N(a.fitnesses), N(b.fitnesses))
+
+
+def test_add_with_extra_scores(dev):
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire, compute_euclidean_centroids
+
+    cent = compute_euclidean_centroids((2, 2), 0.0, 1.0, device=dev)
+    g = torch.rand(4, 8, device=dev)
+    rep = MapElitesRepertoire.init(g, torch.tensor([1.0, 2.0, 3.0, 4.0], device=dev),
+                                   T(np.array([[0.1, 0.1], [0.9, 0.1], [0.1, 0.9], [0.2, 0.2]]), dev), cent,
+                                   extra_scores={"a": torch.arange(4.0, device=dev), "b": torch.ones(4, device=dev)}, keys_extra_scores=("a",))
+    assert set(rep.extra_scores) == {"a"}
+    assert N(rep.extra_scores["a"]).tolist() == [3.0, 1.0, 2.0, 0.0]   # cell 0 won by offspring 3 (fitness 4)
+
+
+# ------------------------------------------------------------------------------------------------- metrics
+def test_default_qd_metrics(dev, co):
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+    from qdax_b200.utils.metrics import default_qd_metrics
+
+    rng = np.random.default_rng(3)
+    for K in (4, 10000, 50000):
+        fit = np.where(rng.random(K) < 0.6, rng.standard_normal(K), -np.inf).astype(np.float32)
+        rep = MapElitesRepertoire(torch.zeros(K, 4, device=dev), T(fit.reshape(-1, 1), dev), torch.zeros(K, 2, device=dev), torch.zeros(K, 2, device=dev))
+        m = default_qd_metrics(rep, qd_offset=1.5)
+        ref = co.metrics(fit, 1.5)
+        assert np.allclose([float(m["qd_score"]), float(m["max_fitness"]), float(m["coverage"])], ref, rtol=1e-6)
+        mn = qn.default_qd_metrics(qn.Repertoire(None, fit.reshape(-1, 1), None, None), 1.5)
+        assert np.isclose(float(m["qd_score"]), float(mn["qd_score"]), rtol=RTOL) and np.isclose(float(m["coverage"]), float(mn["coverage"]), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- full runs
+def _readme_setup(dev, task, B, D, grid_shape, init_n, seed):
+    from qdax_b200 import random as qr
+    from qdax_b200.core.containers.mapelites_repertoire import compute_euclidean_centroids
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+    from qdax_b200.core.map_elites import MAPElites
+    from qdax_b200.tasks.arm import arm_scoring_function
+    from qdax_b200.tasks.standard_functions import rastrigin_scoring_function, sphere_scoring_function
+    from qdax_b200.utils.metrics import default_qd_metrics
+
+    scoring = {"arm": arm_scoring_function, "rastrigin": rastrigin_scoring_function, "sphere": sphere_scoring_function}[task]
+    key = qr.key(seed)
+    key, subkey = qr.split(key)
+    init = qr.uniform(subkey, (init_n, D), minval=0.0, maxval=1.0, device=dev)
+    emitter = MixingEmitter(lambda x, y: (x, y), functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B)
+    me = MAPElites(scoring, emitter, functools.partial(default_qd_metrics, qd_offset=0.0))
+    cent = compute_euclidean_centroids(grid_shape, 0.0, 1.0, device=dev)
+    key, subkey = qr.split(key)
+    rep, state, metrics = me.init(init, cent, subkey)
+    return me, rep, state, key, init, cent
+
+
+def _oracle_init(co, init, cent, task):
+    K, D = cent.shape[0], init.shape[1]
+    f0, d0 = co.score(task, init)
+    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, cent.shape[1])), init, f0, d0, co.cells(d0, cent))
+    return g, f, d
+
+
+@pytest.mark.parametrize("task", ["arm", "rastrigin", "sphere"])
+def test_readme_loop_full_run_bit_exact(dev, co, task):
+    """BASELINE config 1 (README example: D=100, grid 100x100, B=1024, 50 iterations, seed 42), driven exactly like
+    the README: host loop, `key, subkey = split(key)`, `update(repertoire, state, subkey)`.  The whole repertoire
+    after 50 generations equals the oracle's bit for bit; QD metrics within 1e-5."""
+    from qdax_b200 import random as qr
+
+    me, rep, state, key, init, cent = _readme_setup(dev, task, 1024, 100, (100, 100), 100, 42)
+    g, f, d = _oracle_init(co, N(init), N(cent), task)
+    assert np.array_equal(N(rep.genotypes), g) and np.array_equal(N(rep.fitnesses).ravel(), f)
+    okey = np.array(key, dtype=np.uint32)
+    hist = []
+    for i in range(50):
+        key, subkey = qr.split(key)
+        rep, state, metrics = me.update(rep, state, subkey)
+        hist.append([float(metrics["qd_score"]), float(metrics["max_fitness"]), float(metrics["coverage"])])
+    G, F, Dn, k2, M, _ = co.map_elites_scan(g, f, d, N(cent), okey, 50, 1024, task)
+    assert (np.array(key) == k2).all()
+    assert np.array_equal(N(rep.fitnesses).ravel(), F), "insertion decisions / fitnesses differ"
+    assert np.array_equal(N(rep.genotypes), G) and np.array_equal(N(rep.descriptors), Dn)
+    assert np.allclose(np.array(hist, np.float32), M, rtol=RTOL)
+    assert hist[-1][2] > hist[0][2]   # coverage grows
+
+
+def test_scan_matches_update_loop_and_graph(dev, co):
+    from qdax_b200 import lax as qlax
+
+    me, rep, state, key, init, cent = _readme_setup(dev, "arm", 512, 20, (16, 16), 32, 7)
+    g, f, d = _oracle_init(co, N(init), N(cent), "arm")
+    G, F, Dn, k2, M, _ = co.map_elites_scan(g, f, d, N(cent), np.array(key), 12, 512, "arm")
+    for kwargs in ({}, {"graph": True}):
+        (rep2, _, key2), metrics = qlax.scan(me.scan_update, (rep, state, key), (), length=12, **kwargs)
+        assert (np.array(key2) == k2).all()
+        assert np.array_equal(N(rep2.genotypes), G) and np.array_equal(N(rep2.fitnesses).ravel(), F) and np.array_equal(N(rep2.descriptors), Dn)
+        assert np.allclose(N(metrics["qd_score"]), M[:, 0], rtol=RTOL) and np.allclose(N(metrics["coverage"]), M[:, 2], rtol=1e-6)
+    # the python scan_update loop (host key chain) gives the same thing
+    carry = (rep, state, key)
+    for _ in range(12):
+        carry, m = me.scan_update(carry, None)
+    assert np.array_equal(N(carry[0].genotypes), G) and (np.array(carry[2]) == k2).all()
+    assert np.array_equal(N(rep.fitnesses).ravel(), f)   # the initial repertoire was never modified
+
+
+def test_golden_c1mini(dev, golden):
+    from qdax_b200 import lax as qlax
+
+    g = golden
+    me, rep, state, key, init, cent = _readme_setup(dev, "arm", 64, 20, (16, 16), 32, 42)
+    assert np.array_equal(N(init), g["C1mini_init"])
+    (rep2, _, key2), metrics = qlax.scan(me.scan_update, (rep, state, jr.key(5)), (), length=10)
+    assert np.array_equal(N(rep2.genotypes), g["C1mini_g"]) and np.array_equal(N(rep2.fitnesses).ravel(), g["C1mini_f"])
+    assert np.array_equal(N(rep2.descriptors), g["C1mini_d"]) and (np.array(key2) == g["C1mini_key"]).all()
+    assert np.allclose(N(metrics["qd_score"]), g["C1mini_metrics"][:, 0], rtol=RTOL)
+
+
+def test_ask_tell_generic_path_with_python_scoring(dev, co):
+    """ask / user scoring / tell (reference tests/core_test/map_elites_test.py:272-295): a user-supplied Python
+    scoring function still plugs in; emit and add run natively and match the oracle."""
+    me, rep, state, key, init, cent = _readme_setup(dev, "arm", 256, 20, (16, 16), 32, 3)
+    from qdax_b200 import random as qr
+
+    def user_scoring(x):
+        f = -(x - 0.5).pow(2).sum(dim=1)
+        return f, x[:, :2].contiguous()
+
+    g0, f0, d0 = N(rep.genotypes), N(rep.fitnesses).ravel(), N(rep.descriptors)
+    for _ in range(3):
+        key, subkey = qr.split(key)
+        x, info = me.ask(rep, state, subkey)
+        emit_key = jr.split(subkey)[1]
+        xo, _, _ = co.emit_isoline(g0, f0, emit_key, 256, 0.05, 0.1, 0.0, 1.0)
+        assert np.array_equal(N(x), xo)
+        f, d = user_scoring(x)
+        rep, state, metrics = me.tell(x, f, d, rep, state)
+        g0, f0, d0, _ = co.add(g0, f0, d0, xo, N(f), N(d), co.cells(N(d), N(cent)))
+        assert np.array_equal(N(rep.genotypes), g0) and np.array_equal(N(rep.fitnesses).ravel(), f0)
+
+
+def test_cvt_rastrigin_generation_bruteforce_path(dev, co):
+    """BASELINE config 2 shape at reduced size: rastrigin D=100, non-grid (CVT-like) centroids -> brute-force cells."""
+    from qdax_b200 import lax as qlax
+    from qdax_b200 import random as qr
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+    from qdax_b200.core.map_elites import MAPElites
+    from qdax_b200.tasks.standard_functions import rastrigin_scoring_function
+    from qdax_b200.utils.metrics import default_qd_metrics
+
+    K, D, B = 1000, 100, 4096
+    cent = np.random.default_rng(0).random((K, 2)).astype(np.float32)
+    init = N(qr.uniform(jr.key(1), (200, D), device=dev))
+    em = MixingEmitter(lambda x, y: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B)
+    me = MAPElites(rastrigin_scoring_function, em, functools.partial(default_qd_metrics, qd_offset=0.0))
+    rep, state, _ = me.init(T(init, dev), T(cent, dev), jr.key(2))
+    g, f, d = _oracle_init(co, init, cent, "rastrigin")
+    (rep2, _, key2), metrics = qlax.scan(me.scan_update, (rep, state, jr.key(3)), (), length=5)
+    G, F, Dn, k2, M, _ = co.map_elites_scan(g, f, d, cent, jr.key(3), 5, B, "rastrigin")
+    assert np.array_equal(N(rep2.genotypes), G) and np.array_equal(N(rep2.fitnesses).ravel(), F) and (np.array(key2) == k2).all()
+
+
+# ------------------------------------------------------------------------------------------------- full size properties
+def test_full_size_properties_c3(dev):
+    """BASELINE config 3 size on one GPU (B = 2^20, D = 100, grid 100x100): size-independent properties."""
+    from qdax_b200 import lax as qlax
+    from qdax_b200.core.containers.mapelites_repertoire import get_cells_indices
+
+    me, rep, state, key, init, cent = _readme_setup(dev, "arm", 1 << 20, 100, (100, 100), 100, 42)
+    (rep1, _, key1), m1 = qlax.scan(me.scan_update, (rep, state, key), (), length=2)
+    (rep2, _, key2), m2 = qlax.scan(me.scan_update, (rep, state, key), (), length=2)
+    assert torch.equal(rep1.genotypes, rep2.genotypes) and torch.equal(rep1.fitnesses, rep2.fitnesses)   # run-to-run determinism
+    occ = rep1.fitnesses.reshape(-1) != -np.inf
+    # every stored individual lies in its own cell and reproduces its stored fitness / descriptor
+    from qdax_b200.tasks.arm import arm_scoring_function
+    f, d, _ = arm_scoring_function(rep1.genotypes[occ])
+    assert torch.equal(f, rep1.fitnesses.reshape(-1)[occ]) and torch.equal(d, rep1.descriptors[occ])
+    cells = get_cells_indices(rep1.descriptors[occ], cent)
+    assert torch.equal(cells.long(), torch.nonzero(occ).reshape(-1))
+    g = rep1.genotypes[occ]
+    assert float(g.min()) >= 0.0 and float(g.max()) <= 1.0
+    assert float(m1["coverage"][1]) >= float(m1["coverage"][0]) > 0
+    # idempotence at full size
+    again = rep1.add(rep1.genotypes[occ], rep1.descriptors[occ], rep1.fitnesses[occ])
+    assert torch.equal(again.genotypes, rep1.genotypes) and torch.equal(again.fitnesses, rep1.fitnesses)
+
+
+# ------------------------------------------------------------------------------------------------- DNS
+def test_dns_golden_and_random(dev, golden, co):
+    from qdax_b200 import _native
+
+    g = golden
+    out = _native.dns_add(T(g["DNS_pg"], dev), T(g["DNS_pf"], dev), T(g["DNS_pd"], dev), T(g["DNS_bg"], dev), T(g["DNS_bf"], dev), T(g["DNS_bd"], dev), 3)
+    assert np.array_equal(N(out[3]), g["DNS_meta"], equal_nan=True) and np.array_equal(N(out[4]), g["DNS_surv"])
+    assert np.array_equal(N(out[0]), g["DNS_g"]) and np.array_equal(N(out[1]), g["DNS_f"], equal_nan=True)
+    assert np.array_equal(N(out[2]), g["DNS_d"], equal_nan=True)
+    rng = np.random.default_rng(5)
+    for P, B, D, Dd, k in [(1000, 300, 8, 2, 3), (513, 77, 4, 3, 5), (200, 64, 4, 6, 15), (4000, 1024, 12, 2, 1)]:
+        pf = np.where(rng.random(P) < 0.9, np.round(rng.standard_normal(P), 1), -np.inf).astype(np.float32)
+        pd = np.where(np.isinf(pf)[:, None], np.nan, np.round(rng.random((P, Dd)), 2)).astype(np.float32)
+        pg = rng.random((P, D)).astype(np.float32)
+        bf = np.round(rng.standard_normal(B), 1).astype(np.float32)
+        bd, bg = np.round(rng.random((B, Dd)), 2).astype(np.float32), rng.random((B, D)).astype(np.float32)
+        G, F, Dn, meta, surv = co.dns_add(pg, pf, pd, bg, bf, bd, k)
+        out = _native.dns_add(T(pg, dev), T(pf, dev), T(pd, dev), T(bg, dev), T(bf, dev), T(bd, dev), k)
+        assert np.array_equal(N(out[3]), meta, equal_nan=True) and np.array_equal(N(out[4]), surv)
+        assert np.array_equal(N(out[0]), G) and np.array_equal(N(out[1]), F, equal_nan=True)
