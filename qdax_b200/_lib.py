@@ -88,7 +88,16 @@ def lib() -> C.CDLL:
     return _lib
 
 
+# every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
+KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_offer_cells": 1,
+                   "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1,
+                   "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
+launch_count = 0
+
+
 def call(name: str, *args) -> None:
+    global launch_count
+    launch_count += KERNEL_LAUNCHES.get(name, 0)
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise QdxError(name, rc)

@@ -80,24 +80,30 @@ class DistributedMAPElites(MAPElites):
         first = rep.tie_break == "first"
         winners = self._exchange == "winners"
         base = rank * B
+        self._mark("begin")
         _native.select_prepare(rep_f, ws, key_mode, key)
+        self._mark("prepare")
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], Dd, grid, winners and grid is not None, base, first,
                          buf["g"], buf["f"], buf["d"], buf["c"])
         if grid is None:   # cell assignment stays sharded: each rank assigns only its own offspring
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=winners, idx_base=base, first_wins=first, out=buf["c"])
+        self._mark("generate")
         if not winners:
             G = parallel.all_gather_rows(buf["g"], self._group, gb["G"] if R > 1 else None)
             F = parallel.all_gather_rows(buf["f"], self._group, gb["F"] if R > 1 else None)
             Dn = parallel.all_gather_rows(buf["d"], self._group, gb["Dn"] if R > 1 else None)
             Cc = parallel.all_gather_rows(buf["c"], self._group, gb["C"] if R > 1 else None)
+            self._mark("exchange")
             _native.offer_cells(Cc, F, ws, rep_f, 0, first)
             _native.commit(ws, G, F, Dn, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
                            metrics_out=metrics_out)
+            self._mark("commit")
             return
         if R == 1:
             _native.commit(ws, buf["g"], buf["f"], buf["d"], rep.genotypes, rep_f, rep.descriptors, idx_base=base, first_wins=first,
                            qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
+            self._mark("commit")
             return
         keytab = ws.keytab()
         parallel.all_reduce_max_u64_(keytab, self._group)
@@ -106,8 +112,10 @@ class DistributedMAPElites(MAPElites):
         sg, sd, sf = _stage_views(st, D, Dd)
         _native.commit(ws, buf["g"], buf["f"], buf["d"], sg, sf, sd, idx_base=base, first_wins=first, mode=1)
         parallel.all_reduce_disjoint_rows_(st, self._group)
+        self._mark("exchange")
         _native.commit(ws, sg, sf, sd, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
                        metrics_out=metrics_out, mode=2)
+        self._mark("commit")
 
     def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False):
         """reference :92-161.  `key` is this rank's key (examples/distributed_mapelites.ipynb cell 23:
@@ -119,6 +127,7 @@ class DistributedMAPElites(MAPElites):
             rep = repertoire if donate else repertoire._clone_state()
             m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
             self._fused_distributed_generation(rep, cfg, _native.KEYMODE_DIST_UPDATE, key, m)
+            self._last_metrics = m
             return rep, emitter_state, self._metrics_dict(m)
         ks = qrandom.split(key)                                             # :124
         key, subkey = ks[0], ks[1]

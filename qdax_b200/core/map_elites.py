@@ -63,6 +63,7 @@ class MAPElites:
         self._metrics_function = metrics_function
         self._repertoire_init = repertoire_init
         self._buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self._timeline: Optional[list] = None   # bench.py: [(label, cuda event)] recorded around each kernel
 
     # ------------------------------------------------------------------------------------------ fused path
     def _fused_config(self, repertoire) -> Optional[dict]:
@@ -96,6 +97,12 @@ class MAPElites:
             }
         return self._buffers[k]
 
+    def _mark(self, label: str) -> None:
+        if self._timeline is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._timeline.append((label, e))
+
     def _fused_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out: torch.Tensor) -> None:
         """One generation in place on `rep` (launch-only; no host synchronisation)."""
         K, D = rep.genotypes.shape
@@ -105,14 +112,19 @@ class MAPElites:
         rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
         first = rep.tie_break == "first"
+        self._mark("begin")
         _native.select_prepare(rep_f, ws, key_mode, key)
+        self._mark("prepare")
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], cfg["desc_dim"], grid, grid is not None, 0, first,
                          buf["g"], buf["f"], buf["d"], buf["c"])
+        self._mark("generate")
         if grid is None:
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=True, first_wins=first, out=buf["c"])
+            self._mark("cells")
         _native.commit(ws, buf["g"], buf["f"], buf["d"], rep.genotypes, rep_f, rep.descriptors, first_wins=first,
                        qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
+        self._mark("commit")
 
     @staticmethod
     def _metrics_dict(m: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -151,6 +163,7 @@ class MAPElites:
             rep = repertoire if donate else repertoire._clone_state()
             m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
             self._fused_generation(rep, cfg, _native.KEYMODE_UPDATE, key, m)
+            self._last_metrics = m          # (qd_score, max_fitness, coverage, inserted) as one device tensor
             return rep, emitter_state, self._metrics_dict(m)
 
         ks = qrandom.split(key)                                             # :177
