@@ -139,14 +139,19 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def _centroids_np(cfg):
+def _cvt_points(K):
+    """seeded U[0,1)^2 points standing in for k-means centroids (same work)"""
     import numpy as np
 
+    return np.random.default_rng(0).random((K, 2)).astype(np.float32)
+
+
+def _centroids_np(cfg):
+    """CPU legs only (imports the oracle)."""
+    if cfg["cvt"]:
+        return _cvt_points(cfg["K"]), cfg["K"]
     from oracle import qdax_numpy as qn
 
-    if cfg["cvt"]:
-        K = cfg["K"]
-        return np.random.default_rng(0).random((K, 2)).astype(np.float32), K   # seeded U[0,1)^2 points
     cent = qn.compute_euclidean_centroids(cfg["grid"], 0.0, 1.0)
     return cent, cent.shape[0]
 
@@ -209,8 +214,8 @@ def run_gpu(args, cfg):
     else:
         me = MAPElites(scoring, emitter, metrics_fn)
     if cfg["cvt"]:
-        cent_np, K = _centroids_np(cfg)
-        cent = torch.from_numpy(cent_np).to(dev)
+        K = cfg["K"]
+        cent = torch.from_numpy(_cvt_points(K)).to(dev)
     else:
         cent = compute_euclidean_centroids(cfg["grid"], 0.0, 1.0, device=dev)
         K = cent.shape[0]

@@ -9,7 +9,8 @@
  *   - all arithmetic is IEEE-754 binary32, round-to-nearest-even, one rounding per written
  *     operation; fmaf() is used exactly where written; the file must be compiled with
  *     -ffp-contract=off and without fast-math;
- *   - reductions over the genotype / descriptor axis are sequential, left to right;
+ *   - reductions over the genotype axis are sequential, left to right, starting from +0.0f (XLA reduce init);
+ *     squared distances over the descriptor axis start from the first term;
  *   - log1p / sin / cos are the polynomial kernels written in this file (the reference calls
  *     jnp.log1p / jnp.sin / jnp.cos whose last-bit behaviour belongs to jaxlib, which is not
  *     installable here); they agree with libm to ~1 ulp (tests/test_oracle_cross.py).
@@ -68,9 +69,17 @@ static inline uint32_t bits32(qo_key k, uint64_t i) {
     return a ^ b;
 }
 static inline float unit_float(uint32_t bits) { return u2f((bits >> 9) | 0x3F800000u) - 1.0f; }
-/* jnp.clip / jnp.maximum / jnp.minimum written as compares so that NaN propagates (XLA max/min do). */
-static inline float max_nanprop(float x, float lo) { return x < lo ? lo : x; }
-static inline float min_nanprop(float x, float hi) { return x > hi ? hi : x; }
+/* jnp.clip / jnp.maximum / jnp.minimum: NaN propagates (XLA max/min do); -0 < +0 (IEEE 754-2019 maximum/minimum). */
+static inline float max_nanprop(float x, float lo) {
+    if (x != x || lo != lo) return NAN;
+    if (x == lo) return signbit(x) ? lo : x;
+    return x < lo ? lo : x;
+}
+static inline float min_nanprop(float x, float hi) {
+    if (x != x || hi != hi) return NAN;
+    if (x == hi) return signbit(x) ? x : hi;
+    return x > hi ? hi : x;
+}
 
 /* ------------------------------------------------------------------ QDX-F32 spec math */
 /* log(t), t > 0 normal.  t = m * 2^e, m in [sqrt(1/2), sqrt(2)); Cephes-style degree-9 kernel. */
@@ -97,11 +106,12 @@ static inline float spec_logf(float t) {
     res = fmaf(fe, 0.693359375f, res);
     return res;
 }
-/* log1p(y) for y in (-1, 0]:  log(t) + (y - (t - 1)) / t  with t = fl(1 + y). */
+/* log1p(y) for y in (-1, 0]:  log(t) + (y - (t - 1)) * (2 - t)  with t = fl(1 + y).
+ * (y - (t - 1)) is the rounding error of t (exact); (2 - t) stands in for 1/t: the correction is at most half an
+ * ulp of t, and wherever 2 - t is a poor reciprocal (t << 1) |log t| > 0.69 dwarfs it.  t == 1 gives exactly y. */
 static inline float spec_log1pf(float y) {
     float t = 1.0f + y;
-    if (t == 1.0f) return y;
-    float c = (y - (t - 1.0f)) / t;
+    float c = (y - (t - 1.0f)) * (2.0f - t);
     return spec_logf(t) + c;
 }
 /* XLA ErfInv32 (Giles) with fused Horner steps. */
@@ -296,20 +306,20 @@ QO_API int qo_emit_isoline(const float* rep_g, const float* rep_f, int64_t K, in
 static void score_row(int task, const float* p, int64_t D, int64_t Dd, float* f_out, float* desc) {
     if (task == 0) {
         float sum = 0.0f;
-        for (int64_t d = 0; d < D; ++d) { float x = min_nanprop(max_nanprop(p[d], 0.0f), 1.0f); sum = (d == 0) ? x : sum + x; }
+        for (int64_t d = 0; d < D; ++d) { float x = min_nanprop(max_nanprop(p[d], 0.0f), 1.0f); sum = sum + x; }
         float mean = sum / (float)D;
         float sq = 0.0f, th = 0.0f, cs = 0.0f, sn = 0.0f;
         for (int64_t d = 0; d < D; ++d) {
             float x = min_nanprop(max_nanprop(p[d], 0.0f), 1.0f);
             float dev = x - mean;
             float dd = dev * dev;
-            sq = (d == 0) ? dd : sq + dd;
+            sq = sq + dd;
             float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;     /* 2*pi*x - pi */
-            th = (d == 0) ? ang : th + ang;                      /* cumsum */
+            th = th + ang;                                        /* cumsum (running sum from 0) */
             float s, c;
             spec_sincosf(th, &s, &c);
-            cs = (d == 0) ? c : cs + c;
-            sn = (d == 0) ? s : sn + s;
+            cs = cs + c;
+            sn = sn + s;
         }
         float var = sq / (float)D;
         *f_out = -sqrtf(var);
@@ -325,7 +335,7 @@ static void score_row(int task, const float* p, int64_t D, int64_t Dd, float* f_
                 spec_sincosf(0x1.921fb6p+2f * x, &s, &c);
                 term = term - 10.0f * c;
             }
-            acc = (d == 0) ? term : acc + term;
+            acc = acc + term;
         }
         if (task == 1) acc = (float)(10.0 * (double)D) + acc;
         *f_out = -acc;

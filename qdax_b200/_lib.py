@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqdx.so")
+LIB_PATH = os.environ.get("QDX_LIB_PATH", os.path.join(_HERE, "libqdx.so"))   # override: A/B builds of the same ABI
 
 ERRORS = {
     -1: "QDX_ERR_ARG: bad argument",

@@ -153,22 +153,24 @@ QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
 
 constexpr int QDX_GEN_WARPS = 4;
 
-template <int TASK, int GRID_DD>
-__global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const QdxGenParams p) {
+// ARM_CLIP: arm.py:27 clips the genotype to [0,1] before scoring; when the variation already clipped to a range
+// inside [0,1] that clip is the identity and is compiled out (bit-identical result).
+template <int TASK, int GRID_DD, bool ARM_CLIP>
+__global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(const QdxGenParams p) {
     extern __shared__ __align__(128) float s_tiles[];
     __shared__ QdxSeg s_seg[QDX_MAX_SEG];
     __shared__ float s_last[QDX_MAX_SEG];
-    __shared__ float s_axes[GRID_DD > 0 ? QDX_MAX_AXES : 1];
 
     const QdxWorkspace* ws = (const QdxWorkspace*)p.ws;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nseg = ws->sel.nseg;
+    const int32_t D = p.D, DC = p.DC, DS = p.DS;
+    float* s_axes = s_tiles + (size_t)QDX_GEN_WARPS * 32 * DS;      // grid axis values, after the tiles
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
     if (GRID_DD > 0) for (int i = threadIdx.x; i < p.grid.total_axes; i += blockDim.x) s_axes[i] = p.grid.axes[i];
     __syncthreads();
     if (nseg <= 0) return;     // empty repertoire: error flag already raised by prepare
 
-    const int32_t D = p.D, DC = p.DC, DS = p.DS;
     float* tile = s_tiles + (size_t)warp * 32 * DS;
     const int64_t row0 = ((int64_t)blockIdx.x * QDX_GEN_WARPS + warp) * 32;
     if (row0 >= p.B) return;
@@ -180,56 +182,55 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const 
     const float total = ws->sel.total;
 
     // ---- phase 0: parents + line noise, lane = row --------------------------------------------------
-    int32_t p1 = 0, p2 = 0; float line = 0.0f;
-    if (valid) {
+    // (rows past the end of the batch compute harmless values and never store)
+    int32_t p1, p2; float line;
+    {
         float u1 = qdx_unit_float(qdx_bits32(keys.sel1, (uint64_t)row));
         float u2 = qdx_unit_float(qdx_bits32(keys.sel2, (uint64_t)row));
         p1 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u1)) - 1];
         p2 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u2)) - 1];
-        line = qdx_normal_from_bits(qdx_bits32(keys.line, (uint64_t)row)) * p.line_sigma;
-        if (p.out_p1) p.out_p1[row] = p1;
-        if (p.out_p2) p.out_p2[row] = p2;
+        __syncwarp();
+        line = qdx_normal_from_bits_t<true>(qdx_bits32(keys.line, (uint64_t)row)) * p.line_sigma;
+        if (valid && p.out_p1) p.out_p1[row] = p1;
+        if (valid && p.out_p2) p.out_p2[row] = p2;
     }
 
-    // row-serial accumulators (TASK-dependent), carried across chunks
-    float acc0 = 0.0f;
+    float acc0 = 0.0f;        // rastrigin / sphere running sum, carried across chunks
     const int nchunks = (D + DC - 1) / DC;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int d0 = ch * DC;
         const int dc = (D - d0) < DC ? (D - d0) : DC;     // genes in this chunk (multiple of 4)
-        const int q = dc >> 2;
+        const int q = dc >> 2;                            // quads per row in this chunk (<= 32)
+        const uint32_t qmagic = (1u << 20) / (uint32_t)q + 1u;   // qi / q == (qi * qmagic) >> 20 for qi * q < 2^20
         // ---- phase 1: gene-parallel variation over the tile ---------------------------------------------
-        {
-            int r = 0, dq = lane;
-            while (dq >= q) { dq -= q; ++r; }
-            const int total_quads = nrows * q;
-            for (int qi = lane; qi < ((total_quads + 31) & ~31); qi += 32) {
-                const bool act = qi < total_quads;
-                const int rr = act ? r : 0;
-                const int32_t pa = __shfl_sync(0xffffffffu, p1, rr);
-                const int32_t pb = __shfl_sync(0xffffffffu, p2, rr);
-                const float ln = __shfl_sync(0xffffffffu, line, rr);
-                if (act) {
-                    const int d = d0 + (dq << 2);
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pa * D + d));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pb * D + d));
-                    const uint64_t ctr = (uint64_t)(row0 + rr) * (uint64_t)D + (uint64_t)d;
-                    float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, xv[4];
+        // All 32 lanes stay converged (lanes past the end recompute the last quad and skip the store), so the
+        // normal transform can vote with a full mask.  (2x unrolling measured: no gain, profiles/r1_notes.md.)
+        const int total_quads = nrows * q;
+        for (int qb = 0; qb < total_quads; qb += 32) {
+            const bool act = qb + lane < total_quads;
+            const int qi = act ? qb + lane : total_quads - 1;
+            const int rr = (int)(((uint32_t)qi * qmagic) >> 20);
+            const int dq = qi - rr * q;
+            const int32_t pa = __shfl_sync(0xffffffffu, p1, rr);
+            const int32_t pb = __shfl_sync(0xffffffffu, p2, rr);
+            const float ln = __shfl_sync(0xffffffffu, line, rr);
+            const int d = d0 + (dq << 2);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pa * D + d));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pb * D + d));
+            const uint64_t ctr = (uint64_t)(row0 + rr) * (uint64_t)D + (uint64_t)d;
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, xv[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float iso = qdx_normal_from_bits(qdx_bits32(keys.leaf, ctr + j)) * p.iso_sigma;
-                        float t1 = av[j] + iso;
-                        float t2 = bv[j] - av[j];
-                        float t3 = t2 * ln;
-                        float x = t1 + t3;                                  // mutation_operators.py:211
-                        if (p.has_min) x = qdx_max_nanprop(x, p.minv);      // :214-215
-                        if (p.has_max) x = qdx_min_nanprop(x, p.maxv);
-                        xv[j] = x;
-                    }
-                    *reinterpret_cast<float4*>(tile + rr * DS + (dq << 2)) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-                }
-                dq += 32; while (dq >= q) { dq -= q; ++r; }
+            for (int j = 0; j < 4; ++j) {
+                float iso = qdx_normal_from_bits_t<true>(qdx_bits32(keys.leaf, ctr + j)) * p.iso_sigma;
+                float t1 = av[j] + iso;
+                float t2 = bv[j] - av[j];
+                float t3 = t2 * ln;
+                float x = t1 + t3;                                  // mutation_operators.py:211
+                if (p.has_min) x = qdx_max_nanprop(x, p.minv);      // :214-215
+                if (p.has_max) x = qdx_min_nanprop(x, p.maxv);
+                xv[j] = x;
             }
+            if (act) *reinterpret_cast<float4*>(tile + rr * DS + (dq << 2)) = make_float4(xv[0], xv[1], xv[2], xv[3]);
         }
         // ---- phase 3 (issued early): tile -> global through the bulk-copy engine ------------------------
         // writers make their generic-proxy stores visible to the async proxy, then the warp syncs, then issue
@@ -243,18 +244,19 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const 
             }
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
-        // ---- phase 2: row-serial scoring, lane = row ---------------------------------------------------
+        // ---- phase 2: row-serial scoring, lane = row; sums run left to right from +0 (the spec) ----------
         if (TASK != QDX_TASK_NONE && valid) {
             const float* xr = tile + lane * DS;
             if (TASK == QDX_TASK_ARM) {        // single chunk guaranteed by the launcher
                 float sum = 0.0f;
+#pragma unroll 5
                 for (int d = 0; d < dc; d += 4) {
                     float4 v = *reinterpret_cast<const float4*>(xr + d);
                     float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float x = qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f);
-                        sum = (d + j == 0) ? x : sum + x;
+                        float x = ARM_CLIP ? qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f) : xs[j];
+                        sum = sum + x;
                     }
                 }
                 const float mean = __fdiv_rn(sum, (float)D);
@@ -262,16 +264,20 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const 
                 for (int d = 0; d < dc; d += 4) {
                     float4 v = *reinterpret_cast<const float4*>(xr + d);
                     float xs[4] = {v.x, v.y, v.z, v.w};
+                    float thj[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float x = qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f);
+                    for (int j = 0; j < 4; ++j) {          // the serial chains: variance sum and joint-angle cumsum
+                        float x = ARM_CLIP ? qdx_min_nanprop(qdx_max_nanprop(xs[j], 0.0f), 1.0f) : xs[j];
                         float dev = x - mean;
-                        float dd = dev * dev;
-                        float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;
-                        float s, c;
-                        if (d + j == 0) { sq = dd; th = ang; qdx_sincosf(th, s, c); cs = c; sn = s; }
-                        else { sq = sq + dd; th = th + ang; qdx_sincosf(th, s, c); cs = cs + c; sn = sn + s; }
+                        sq = sq + dev * dev;
+                        th = th + (0x1.921fb6p+2f * x - 0x1.921fb6p+1f);
+                        thj[j] = th;
                     }
+                    float sj[4], cj[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) qdx_sincosf(thj[j], sj[j], cj[j]);   // 4 independent evaluations (ILP)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { cs = cs + cj[j]; sn = sn + sj[j]; }
                 }
                 const float fit = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
                 const float dx = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
@@ -288,17 +294,19 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32) qdx_generate_kernel(const 
                 for (int d = 0; d < dc; d += 4) {
                     float4 v = *reinterpret_cast<const float4*>(xr + d);
                     float xs[4] = {v.x, v.y, v.z, v.w};
+                    float term[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float x = xs[j] * 10.0f - 5.0f;
-                        float term = x * x;
+                        term[j] = x * x;
                         if (TASK == QDX_TASK_RASTRIGIN) {
                             float s, c;
                             qdx_sincosf(0x1.921fb6p+2f * x, s, c);
-                            term = term - 10.0f * c;
+                            term[j] = term[j] - 10.0f * c;
                         }
-                        acc0 = (d0 + d + j == 0) ? term : acc0 + term;
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc0 = acc0 + term[j];
                 }
                 if (ch == 0) {
                     for (int j = 0; j < p.desc_dim; ++j) p.out_d[row * p.desc_dim + j] = xr[j];   // desc = first genes
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict_
                 if (pass == 0) {
                     for (int d = 0; d < dc; ++d) {
                         float x = qdx_min_nanprop(qdx_max_nanprop(xr[d], 0.0f), 1.0f);
-                        sum = (d0 + d == 0) ? x : sum + x;
+                        sum = sum + x;
                     }
                 } else {
                     for (int d = 0; d < dc; ++d) {
@@ -368,8 +376,7 @@ __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict_
                         float dd = dev * dev;
                         float ang = 0x1.921fb6p+2f * x - 0x1.921fb6p+1f;
                         float s, c;
-                        if (d0 + d == 0) { sq = dd; th = ang; qdx_sincosf(th, s, c); cs = c; sn = s; }
-                        else { sq = sq + dd; th = th + ang; qdx_sincosf(th, s, c); cs = cs + c; sn = sn + s; }
+                        sq = sq + dd; th = th + ang; qdx_sincosf(th, s, c); cs = cs + c; sn = sn + s;
                     }
                 }
             } else {
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict_
                     float x = xr[d] * 10.0f - 5.0f;
                     float term = x * x;
                     if (TASK == QDX_TASK_RASTRIGIN) { float s, c; qdx_sincosf(0x1.921fb6p+2f * x, s, c); term = term - 10.0f * c; }
-                    acc = (d0 + d == 0) ? term : acc + term;
+                    acc = acc + term;
                     if (d0 + d < desc_dim) out_d[row * desc_dim + d0 + d] = xr[d];
                 }
             }
@@ -716,13 +723,13 @@ static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
     return 0;
 }
 
-template <int TASK>
+template <int TASK, bool ARM_CLIP>
 static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, cudaStream_t st) {
 #define QDX_LAUNCH_GEN(GD)                                                                                         \
     do {                                                                                                           \
-        cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<TASK, GD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<TASK, GD, ARM_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return (int)e;                                                                       \
-        qdx_generate_kernel<TASK, GD><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);                                  \
+        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);                        \
     } while (0)
     const int gd = (TASK == QDX_TASK_NONE) ? 0 : p.grid.dd;
     switch (gd) {
@@ -737,7 +744,6 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, c
     QDX_CHECK_LAUNCH();
     return 0;
 }
-
 
 extern "C" {
 
@@ -814,13 +820,16 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
     p.iso_sigma = iso_sigma; p.line_sigma = line_sigma; p.has_min = has_min; p.has_max = has_max; p.minv = minval; p.maxv = maxval;
     p.out_g = out_genotypes; p.out_f = out_fitness; p.out_d = out_desc; p.out_cell = out_cells; p.out_p1 = out_p1; p.out_p2 = out_p2;
     p.desc_dim = desc_dim; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
-    const size_t smem = (size_t)QDX_GEN_WARPS * 32 * p.DS * sizeof(float);
+    const size_t smem = ((size_t)QDX_GEN_WARPS * 32 * p.DS + (size_t)p.grid.total_axes) * sizeof(float);
     const dim3 g((unsigned)((B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32)));
+    // arm.py:27 clip(params, 0, 1) is the identity when the variation already clipped into [0, 1]
+    const bool arm_clip = !(has_min && has_max && minval >= 0.0f && maxval <= 1.0f);
     switch (task) {
-        case QDX_TASK_NONE: return launch_generate_task<QDX_TASK_NONE>(p, smem, g, S(stream));
-        case QDX_TASK_ARM: return launch_generate_task<QDX_TASK_ARM>(p, smem, g, S(stream));
-        case QDX_TASK_RASTRIGIN: return launch_generate_task<QDX_TASK_RASTRIGIN>(p, smem, g, S(stream));
-        default: return launch_generate_task<QDX_TASK_SPHERE>(p, smem, g, S(stream));
+        case QDX_TASK_NONE: return launch_generate_task<QDX_TASK_NONE, false>(p, smem, g, S(stream));
+        case QDX_TASK_ARM: return arm_clip ? launch_generate_task<QDX_TASK_ARM, true>(p, smem, g, S(stream))
+                                           : launch_generate_task<QDX_TASK_ARM, false>(p, smem, g, S(stream));
+        case QDX_TASK_RASTRIGIN: return launch_generate_task<QDX_TASK_RASTRIGIN, false>(p, smem, g, S(stream));
+        default: return launch_generate_task<QDX_TASK_SPHERE, false>(p, smem, g, S(stream));
     }
 }
 

@@ -37,6 +37,8 @@ QDX_DEV void qdx_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1
     o0 = x0; o1 = x1;
 }
 
+// (Measured and rejected, profiles/r1_notes.md: issuing the rotations on the FMA pipe as IMAD.WIDE by 2^r + one LOP3
+//  is 22 % slower on B200 -- the wide multiply is not full-rate -- so the funnel shift stays.)
 // jax.random.split(key, n)[i]
 QDX_DEV QdxKey qdx_split(QdxKey k, uint64_t i) {
     QdxKey o;
@@ -51,9 +53,9 @@ QDX_DEV uint32_t qdx_bits32(QdxKey k, uint64_t i) {
 }
 QDX_DEV float qdx_unit_float(uint32_t bits) { return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f; }
 
-// jnp.maximum / jnp.minimum as compares: NaN propagates like XLA max/min.
-QDX_DEV float qdx_max_nanprop(float x, float lo) { return x < lo ? lo : x; }
-QDX_DEV float qdx_min_nanprop(float x, float hi) { return x > hi ? hi : x; }
+// jnp.maximum / jnp.minimum: NaN propagates like XLA max/min, -0 < +0 (IEEE 754-2019 maximum / minimum): FMNMX.NAN.
+QDX_DEV float qdx_max_nanprop(float x, float lo) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo)); return r; }
+QDX_DEV float qdx_min_nanprop(float x, float hi) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(hi)); return r; }
 
 // log(t), t > 0 normal: t = m * 2^e, m in [sqrt(1/2), sqrt(2)).
 QDX_DEV float qdx_logf(float t) {
@@ -79,18 +81,21 @@ QDX_DEV float qdx_logf(float t) {
     res = __fmaf_rn(fe, 0.693359375f, res);
     return res;
 }
-// log1p(y), y in (-1, 0]
+// log1p(y), y in (-1, 0]: log(t) + (y - (t - 1)) * (2 - t), t = fl(1 + y); branch- and division-free
 QDX_DEV float qdx_log1pf(float y) {
     float t = 1.0f + y;
-    if (t == 1.0f) return y;
-    float c = __fdiv_rn(y - (t - 1.0f), t);
+    float c = (y - (t - 1.0f)) * (2.0f - t);
     return qdx_logf(t) + c;
 }
-// XLA ErfInv32 (Giles), fused Horner.
-QDX_DEV float qdx_erfinvf(float x) {
+// XLA ErfInv32 (Giles), fused Horner.  EDGE: handle |x| == 1 (never produced by jax.random.normal's uniform).
+// The tail polynomial (w >= 5, 0.3 % of draws) is entered by a warp-uniform vote so the common path is straight-line.
+// FULLWARP: the caller guarantees all 32 lanes are converged here (saves the activemask query).
+template <bool EDGE, bool FULLWARP>
+QDX_DEV float qdx_erfinvf_t(float x) {
     float w = -qdx_log1pf(-(x * x));
     float p;
-    if (w < 5.0f) {
+    const bool central = w < 5.0f;
+    if (__all_sync(FULLWARP ? 0xffffffffu : __activemask(), central)) {
         w = w - 2.5f;
         p = 2.81022636e-08f;
         p = __fmaf_rn(p, w, 3.43273939e-07f);
@@ -102,28 +107,32 @@ QDX_DEV float qdx_erfinvf(float x) {
         p = __fmaf_rn(p, w, 0.246640727f);
         p = __fmaf_rn(p, w, 1.50140941f);
     } else {
-        w = __fsqrt_rn(w) - 3.0f;
-        p = -0.000200214257f;
-        p = __fmaf_rn(p, w, 0.000100950558f);
-        p = __fmaf_rn(p, w, 0.00134934322f);
-        p = __fmaf_rn(p, w, -0.00367342844f);
-        p = __fmaf_rn(p, w, 0.00573950773f);
-        p = __fmaf_rn(p, w, -0.0076224613f);
-        p = __fmaf_rn(p, w, 0.00943887047f);
-        p = __fmaf_rn(p, w, 1.00167406f);
-        p = __fmaf_rn(p, w, 2.83297682f);
+        // mixed warp: both polynomials share one Horner chain with per-lane coefficients
+        w = central ? w - 2.5f : __fsqrt_rn(w) - 3.0f;
+        p = central ? 2.81022636e-08f : -0.000200214257f;
+        p = __fmaf_rn(p, w, central ? 3.43273939e-07f : 0.000100950558f);
+        p = __fmaf_rn(p, w, central ? -3.5233877e-06f : 0.00134934322f);
+        p = __fmaf_rn(p, w, central ? -4.39150654e-06f : -0.00367342844f);
+        p = __fmaf_rn(p, w, central ? 0.00021858087f : 0.00573950773f);
+        p = __fmaf_rn(p, w, central ? -0.00125372503f : -0.0076224613f);
+        p = __fmaf_rn(p, w, central ? -0.00417768164f : 0.00943887047f);
+        p = __fmaf_rn(p, w, central ? 0.246640727f : 1.00167406f);
+        p = __fmaf_rn(p, w, central ? 1.50140941f : 2.83297682f);
     }
-    if (fabsf(x) == 1.0f) return x * 3.40282347e+38f;
+    if (EDGE && fabsf(x) == 1.0f) return x * 3.40282347e+38f;
     return p * x;
 }
+QDX_DEV float qdx_erfinvf(float x) { return qdx_erfinvf_t<true, false>(x); }
 // jax.random.normal from one 32-bit draw.
-QDX_DEV float qdx_normal_from_bits(uint32_t bits) {
+template <bool FULLWARP>
+QDX_DEV float qdx_normal_from_bits_t(uint32_t bits) {
     const float lo = -0x1.fffffep-1f;
     float f = qdx_unit_float(bits);
     float u = f * 2.0f + lo;
     u = u < lo ? lo : u;
-    return 0x1.6a09e6p+0f * qdx_erfinvf(u);
+    return 0x1.6a09e6p+0f * qdx_erfinvf_t<false, FULLWARP>(u);   // u in [lo, 1): |u| == 1 impossible
 }
+QDX_DEV float qdx_normal_from_bits(uint32_t bits) { return qdx_normal_from_bits_t<false>(bits); }
 // sin & cos: 3-term Cody-Waite by pi/2 (fused), minimax kernels on [-pi/4, pi/4].
 QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
     float q = rintf(th * 0x1.45f306p-1f);

@@ -62,7 +62,7 @@ def all_equal(x: torch.Tensor, group=None) -> bool:
     _, size = world(group)
     if size == 1:
         return True
-    v = x.contiguous().view(torch.uint8).to(torch.int64)
+    v = x.contiguous().view(torch.uint8).reshape(-1).to(torch.int64)
     chk = torch.stack([v.sum(), (v * (torch.arange(v.numel(), device=v.device) % 65521 + 1)).sum()])
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
