@@ -136,7 +136,7 @@ def run_reference(args, cfg):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_coverage": float(m[-1, 2]),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _cvt_points(K):
@@ -358,7 +358,7 @@ def run_gpu(args, cfg):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -390,7 +390,24 @@ def cpu_baseline(cfg, args):
             "label": "C/OpenMP restatement of QDax 0.5.1 (not jax[cpu])"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # library chatter on fd 1 (e.g. "NCCL version ...") -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
