@@ -30,6 +30,8 @@ CONFIGS = {
     "c1": dict(task="arm", D=100, grid=(100, 100), B=1024, cvt=False, note="BASELINE configs[0] (README example)"),
     "c2": dict(task="rastrigin", D=100, K=10000, B=65536, cvt=True, note="BASELINE configs[1] (CVT 10k, brute-force cells)"),
     "c3": dict(task="arm", D=100, grid=(100, 100), B=1 << 20, cvt=False, note="BASELINE configs[2] (arm 100-DoF, batch 2^20)"),
+    "c4": dict(task="sphere", D=1000, K=50000, Dd=32, B=65536, cvt=True,
+               note="BASELINE configs[3] (sphere 1000-D, desc = p[:32] (declared extension), 50k centroids, tensor-core cell assignment)"),
 }
 METRIC = "offspring evaluated+inserted/sec"
 UNIT = "offspring/s"
@@ -114,9 +116,10 @@ def run_reference(args, cfg):
     D, task = cfg["D"], cfg["task"]
     B = min(cfg["B"], args.cpu_sample)
     cent, K = _centroids_np(cfg)
+    Dd = cfg.get("Dd", 2)
     init = co.uniform(jr.split(jr.key(42))[1], 100 * D).reshape(100, D)
-    f0, d0 = co.score(task, init)
-    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, 2)), init, f0, d0, co.cells(d0, cent))
+    f0, d0 = co.score(task, init, Dd)
+    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, Dd)), init, f0, d0, co.cells(d0, cent))
     key = jr.key(7)
     g, f, d, key, _, _ = co.map_elites_scan(g, f, d, cent, key, args.warmup, B, task)
     t0 = time.perf_counter()
@@ -139,17 +142,17 @@ def run_reference(args, cfg):
     emit(line)
 
 
-def _cvt_points(K):
-    """seeded U[0,1)^2 points standing in for k-means centroids (same work)"""
+def _cvt_points(K, Dd=2):
+    """seeded U[0,1)^Dd points standing in for k-means centroids (same work)"""
     import numpy as np
 
-    return np.random.default_rng(0).random((K, 2)).astype(np.float32)
+    return np.random.default_rng(0).random((K, Dd)).astype(np.float32)
 
 
 def _centroids_np(cfg):
     """CPU legs only (imports the oracle)."""
     if cfg["cvt"]:
-        return _cvt_points(cfg["K"]), cfg["K"]
+        return _cvt_points(cfg["K"], cfg.get("Dd", 2)), cfg["K"]
     from oracle import qdax_numpy as qn
 
     cent = qn.compute_euclidean_centroids(cfg["grid"], 0.0, 1.0)
@@ -161,7 +164,7 @@ def _config_dict(args, cfg, B_step):
     return {"workload": f"MAP-Elites {cfg['task']} {cfg['D']}-D, K={K} {'CVT(seeded uniform)' if cfg['cvt'] else 'grid'} cells, "
                         f"batch {cfg['B']} per generation, iso 0.05 / line 0.1 / clip [0,1]; {cfg['note']}",
             "name": args.config, "global_batch": cfg["B"], "batch_per_step": B_step, "genotype_dim": cfg["D"], "cells": K,
-            "descriptor_dim": 2, "parallelism": f"dp{args.gpus} (offspring sharded, repertoire replicated)",
+            "descriptor_dim": cfg.get("Dd", 2), "parallelism": f"dp{args.gpus} (offspring sharded, repertoire replicated)",
             "exchange": args.exchange if args.gpus > 1 else "none", "l2": "working set > L2 (offspring buffer 400 B x batch)"
             if cfg["B"] * cfg["D"] * 4 > 126e6 else "L2 flushed between steps by a 256 MB write" if args.flush_l2 else "working set fits L2; not flushed"}
 
@@ -182,7 +185,7 @@ def run_gpu(args, cfg):
     from qdax_b200.core.emitters.standard_emitters import MixingEmitter
     from qdax_b200.core.map_elites import MAPElites
     from qdax_b200.tasks.arm import arm_scoring_function
-    from qdax_b200.tasks.standard_functions import rastrigin_scoring_function
+    from qdax_b200.tasks.standard_functions import rastrigin_scoring_function, sphere_scoring_function
     from qdax_b200.utils.metrics import default_qd_metrics
 
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +209,9 @@ def run_gpu(args, cfg):
     D, task, B_total = cfg["D"], cfg["task"], cfg["B"]
     assert B_total % world == 0
     B = B_total // world
-    scoring = {"arm": arm_scoring_function, "rastrigin": rastrigin_scoring_function}[task]
+    Dd = cfg.get("Dd", 2)
+    scoring = {"arm": arm_scoring_function, "rastrigin": rastrigin_scoring_function,
+               "sphere": functools.partial(sphere_scoring_function, desc_dim=Dd)}[task]
     emitter = MixingEmitter(lambda x, k: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B)
     metrics_fn = functools.partial(default_qd_metrics, qd_offset=0.0)
     if world > 1:
@@ -215,7 +220,7 @@ def run_gpu(args, cfg):
         me = MAPElites(scoring, emitter, metrics_fn)
     if cfg["cvt"]:
         K = cfg["K"]
-        cent = torch.from_numpy(_cvt_points(K)).to(dev)
+        cent = torch.from_numpy(_cvt_points(K, Dd)).to(dev)
     else:
         cent = compute_euclidean_centroids(cfg["grid"], 0.0, 1.0, device=dev)
         K = cent.shape[0]
@@ -322,14 +327,15 @@ def run_gpu(args, cfg):
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "of measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "of fallback")
-    ab = algorithmic_bytes(D, 2)
+    ab = algorithmic_bytes(D, Dd)
     dom = max((k for k in kern_ms if k in ("generate", "cells")), key=lambda k: kern_ms[k])
+    cells_kernel = "qdx_cells_tc_kernel (tcgen05 TF32 + exact re-rank)" if Dd >= 8 else "qdx_cells_bf_kernel"
     if dom == "generate":
         dom_bytes = ab["generate_per_offspring"] * B
     else:
-        dom_bytes = (4 * 2 + 4) * B + K * 2 * 4
+        dom_bytes = (4 * Dd + 4) * B + K * Dd * 4
     dom_gbs = dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
-    roofline = {"kernel": {"generate": "qdx_generate_kernel", "cells": "qdx_cells_bf_kernel"}[dom], "bound": "hbm", "achieved": dom_gbs,
+    roofline = {"kernel": {"generate": "qdx_generate_kernel", "cells": cells_kernel}[dom], "bound": "hbm", "achieved": dom_gbs,
                 "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kern_ms[dom],
                 "note": "ALU-bound kernel (one Threefry-2x32-20 block + erfinv per gene, sincos per joint): the HBM fraction is low by construction; see DESIGN.md section 6"}
@@ -374,9 +380,10 @@ def cpu_baseline(cfg, args):
     D, task = cfg["D"], cfg["task"]
     B = min(cfg["B"], args.cpu_sample)
     cent, K = _centroids_np(cfg)
+    Dd = cfg.get("Dd", 2)
     init = co.uniform(jr.split(jr.key(42))[1], 100 * D).reshape(100, D)
-    f0, d0 = co.score(task, init)
-    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, 2)), init, f0, d0, co.cells(d0, cent))
+    f0, d0 = co.score(task, init, Dd)
+    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, Dd)), init, f0, d0, co.cells(d0, cent))
     t0 = time.perf_counter()
     g, f, d, key, _, _ = co.map_elites_scan(g, f, d, cent, jr.key(7), 1, B, task)
     t1 = time.perf_counter() - t0

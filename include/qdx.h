@@ -88,6 +88,17 @@ int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centr
               int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
               uint32_t idx_base, int32_t first_wins, void* stream);
 
+/* ---- stage (c) on the tensor cores, for high-dimensional CVT descriptors (desc_dim <= 32): same result as
+ * qdx_cells (bit-exact argmin of the reference expression): tcgen05 TF32 pass -> candidates within a proven error
+ * band -> exact FP32 re-rank; unresolved rows take an exact brute-force pass.
+ * qdx_cells_tc_workspace: sizes (in elements) of the per-tessellation `prep` float buffer and the per-call int32
+ * `scratch`.  qdx_cells_tc_prepare: one-off per tessellation (swizzled centroid copy, ||c||^2, max ||c||^2). */
+int qdx_cells_tc_workspace(int64_t K, int64_t B, int64_t* prep_floats, int64_t* scratch_ints);
+int qdx_cells_tc_prepare(const float* centroids, int64_t K, int32_t desc_dim, float* prep, void* stream);
+int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const float* prep,
+                 int32_t* scratch, int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
+                 uint32_t idx_base, int32_t first_wins, void* stream);
+
 /* ---- stage (d): MapElitesRepertoire.add (mapelites_repertoire.py:173-266).
  * qdx_offer_cells: segment_max + tie-break as a packed (fitness-key, index) 64-bit atomicMax per cell.
  * qdx_commit: scatter of the winners' genotype / fitness / descriptor rows into the repertoire (in place),

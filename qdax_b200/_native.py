@@ -186,10 +186,48 @@ def score(task: str, g: torch.Tensor, desc_dim: int = 2) -> Tuple[torch.Tensor, 
     return f, d
 
 
+TC_MIN_DIM, TC_MAX_DIM, TC_MIN_CENTROIDS = 8, 32, 1024     # where the tensor-core pass pays off
+
+
+def tc_prep_of(centroids: torch.Tensor) -> torch.Tensor:
+    """Per-tessellation buffers of the tensor-core cell assignment (swizzled centroid copy, norms), cached on the
+    centroid tensor like the grid descriptor."""
+    cache = getattr(centroids, "_qdx_tc_cache", None)
+    ver = (centroids.data_ptr(), centroids._version, tuple(centroids.shape))
+    if cache is None or cache[0] != ver:
+        K, Dd = centroids.shape
+        nf, ni = C.c_int64(0), C.c_int64(0)
+        call("qdx_cells_tc_workspace", C.c_int64(K), C.c_int64(0), C.byref(nf), C.byref(ni))
+        prep = torch.empty(nf.value, dtype=torch.float32, device=centroids.device)
+        call("qdx_cells_tc_prepare", _ptr(centroids), C.c_int64(K), C.c_int32(Dd), _ptr(prep), _stream())
+        cache = (ver, prep)
+        try:
+            centroids._qdx_tc_cache = cache
+        except AttributeError:
+            pass
+    return cache[1]
+
+
+def cells_tc(desc: torch.Tensor, centroids: torch.Tensor, ws: Optional["Workspace"] = None, rep_f=None, fitness=None,
+             offer: bool = False, idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """get_cells_indices through the tcgen05 pass + exact re-rank (desc_dim <= 32)."""
+    B, Dd = desc.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int32, device=desc.device)
+    prep = tc_prep_of(centroids)
+    scratch = torch.empty(B + 64, dtype=torch.int32, device=desc.device)
+    call("qdx_cells_tc", _ptr(desc), C.c_int64(B), C.c_int32(Dd), _ptr(centroids), C.c_int64(centroids.shape[0]), _ptr(prep),
+         _ptr(scratch), _ptr(out), C.c_void_p(0) if ws is None else ws.ptr, _ptr(rep_f), _ptr(fitness), C.c_int32(bool(offer)),
+         C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _stream())
+    return out
+
+
 def cells(desc: torch.Tensor, centroids: torch.Tensor, grid: Optional[Grid] = None, ws: Optional[Workspace] = None,
           rep_f: Optional[torch.Tensor] = None, fitness: Optional[torch.Tensor] = None, offer: bool = False,
-          idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None, allow_tc: bool = True) -> torch.Tensor:
     B, Dd = desc.shape
+    if grid is None and allow_tc and TC_MIN_DIM <= Dd <= TC_MAX_DIM and centroids.shape[0] >= TC_MIN_CENTROIDS and B > 0:
+        return cells_tc(desc, centroids, ws, rep_f, fitness, offer, idx_base, first_wins, out)
     if out is None:
         out = torch.empty(B, dtype=torch.int32, device=desc.device)
     call("qdx_cells", _ptr(desc), C.c_int64(B), C.c_int32(Dd), _ptr(centroids), C.c_int64(centroids.shape[0]), _grid_ptr(grid),

@@ -1,0 +1,404 @@
+// Nearest-centroid cell assignment for high-dimensional CVT descriptors on the 5th-gen tensor cores (sm_100a).
+//
+// Reference semantics (get_cells_indices, qdax/core/containers/mapelites_repertoire.py:111-137 under
+// /root/reference): argmin_k sum_d (x_d - c_kd)^2 in float32, sequential over d, FIRST minimum.  The reference
+// never expands the square; neither does the final decision here:
+//
+//   1. tensor pass   d~(i,k) = ||c_k||^2 - 2 x_i . c_k   with x . c from tcgen05.mma kind::tf32 (M=128, N=256, K=32:
+//                    four K=8 steps), FP32 accumulators in TMEM, double buffered; centroid tiles stream through a
+//                    3-stage shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier
+//                    complete_tx) from a copy of the centroids that was written ONCE in the 128-byte-swizzled
+//                    K-major layout the UMMA descriptors expect (a 32-float row is exactly one swizzle row, so no
+//                    tensor map is needed); warp roles: 1 copy-issuer, 1 MMA-issuer, 4 epilogue warps (one TMEM
+//                    lane quadrant each, thread = descriptor row).
+//   2. candidates    every k with d~ <= min_k d~ + band_i is kept (sorted list of T), where band_i bounds twice the
+//                    TF32 error (|x~c~ - xc| <= 2^-9 |xc| per product, Cauchy-Schwarz over the row) plus twice the
+//                    rounding error of the reference's own float32 sum -- so the list provably contains every index
+//                    that can attain the reference's computed minimum.
+//   3. exact re-rank the candidates are re-evaluated with the reference expression (sub, mul, sequential add) and the
+//                    minimum is taken with the lowest index on ties.  A row whose list is full (possible overflow)
+//                    or whose descriptor is not finite is resolved by an exact brute-force pass.
+//
+// Bit-exact against the oracle (tests/test_gpu_parity.py::test_cells_tensor_core_path).
+#include "qdx_common.cuh"
+#include "../../include/qdx.h"
+
+#define QDX_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+namespace tc {
+
+constexpr int KD = 32;                 // padded descriptor dimension = one 128-byte swizzle row of float32
+constexpr int TILE_M = 128;            // descriptor rows per CTA (UMMA M)
+constexpr int TILE_N = 256;            // centroids per MMA (UMMA N)
+constexpr int STAGES = 3;              // shared-memory ring of centroid tiles
+constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (2 x 256 columns = all 512)
+constexpr int TLIST = 8;               // candidates kept per row
+constexpr int A_BYTES = TILE_M * KD * 4;        // 16 KB
+constexpr int B_BYTES = TILE_N * KD * 4;        // 32 KB
+constexpr int NUM_THREADS = 192;       // warp 0: copies, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// ---- bulk async copy global -> shared, completion on an mbarrier ----------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// ---- tcgen05 ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread t of the warp <-> TMEM lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // start address, 16-byte units          bits [0,14)
+    d |= (uint64_t)1 << 16;                                // leading byte offset (unused: 1)       bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset between 8-row atoms bits [32,46)
+    d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)        bits [46,48)
+    d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B              bits [61,64)
+    return d;
+}
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128.
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+// byte offset of 16-byte chunk `c` of row `r` inside a tile whose base is 1024-byte aligned (Swizzle<3,4,3>)
+__device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------------------
+// one-off per tessellation: swizzled, zero-padded copy of the centroids + ||c||^2 (+inf for padding) + max ||c||
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* __restrict__ cent, int64_t K, int32_t Dd,
+                                                                   int64_t Kpad, float* __restrict__ cs, float* __restrict__ cn,
+                                                                   float* __restrict__ cmax2) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    float row[tc::KD];
+    float n2 = 0.0f;
+#pragma unroll
+    for (int d = 0; d < tc::KD; ++d) {
+        row[d] = (k < K && d < Dd) ? cent[k * Dd + d] : 0.0f;
+        n2 = __fmaf_rn(row[d], row[d], n2);
+    }
+    const int64_t tile = k / tc::TILE_N;
+    const uint32_t r = (uint32_t)(k % tc::TILE_N);
+    char* base = (char*)cs + tile * tc::B_BYTES;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(base + tc::sw128_offset(r, c)) = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+    cn[k] = (k < K) ? n2 : INFINITY;
+    if (k < K) atomicMax(reinterpret_cast<int*>(cmax2), __float_as_int(n2));     // n2 >= 0: int order == float order
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct QdxTcParams {
+    const float* desc; int64_t B; int32_t Dd;
+    const float* cent; int64_t K; int64_t Kpad;
+    const float* cs; const float* cn; const float* cmax2;
+    int32_t* cells; int32_t* fallback_rows; int32_t* fallback_count;
+    void* ws; const float* rep_f; const float* fit; int32_t offer; uint32_t idx_base; int32_t first_wins;
+};
+
+// the reference expression, sequential over d; fully unrolled so that x[] stays in registers
+template <int DDPAD>
+__device__ __forceinline__ float qdx_exact_dist(const float (&x)[DDPAD], const float* __restrict__ c, int Dd) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DDPAD; ++d) {
+        if (d < Dd) { float df = x[d] - __ldg(c + d); float s = df * df; acc = d ? acc + s : s; }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const QdxTcParams p) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-byte alignment
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + A_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + A_BYTES + STAGES * B_BYTES);
+    uint64_t* full = bars;                       // [STAGES]  copies landed
+    uint64_t* empty = bars + STAGES;             // [STAGES]  MMA finished reading the stage
+    uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES] accumulator ready
+    uint64_t* acc_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC_STAGES] accumulator drained by the epilogue
+    uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+    const int ntiles = (int)(p.Kpad / TILE_N);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }   // 4 epilogue warps
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, 512);
+    // A tile: 128 descriptor rows, zero-padded to 32 floats, written in the swizzled layout by all threads
+    for (int i = threadIdx.x; i < TILE_M * 8; i += NUM_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        const int64_t row = row0 + r;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int d = 4 * c + j; v[j] = (row < p.B && d < p.Dd) ? p.desc[row * p.Dd + d] : 0.0f; }
+        *reinterpret_cast<float4*>(sA + sw128_offset(r, c)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== copy issuer =====
+        if (lane == 0) {
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % STAGES; const uint32_t ph = (t / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], B_BYTES);
+                bulk_g2s(sB + s * B_BYTES, (const char*)p.cs + (int64_t)t * B_BYTES, B_BYTES, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint64_t desc_a = make_desc_sw128(smem_u32(sA));
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % STAGES; const uint32_t ph = (t / STAGES) & 1;
+                const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
+                mbar_wait(&acc_empty[a], aph ^ 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t desc_b = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < KD / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 x 16 B
+                    mma_tf32(tmem_base + a * TILE_N, desc_a + 2 * k, desc_b + 2 * k, IDESC, k > 0 ? 1u : 0u);
+                tc_commit(&empty[s]);        // frees the shared-memory stage once the MMAs have read it
+                tc_commit(&acc_full[a]);     // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: thread = descriptor row; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int64_t row = row0 + r;
+        const bool valid = row < p.B;
+        float x[KD];
+        float xn2 = 0.0f; bool finite = true;
+#pragma unroll
+        for (int d = 0; d < KD; ++d) {
+            x[d] = (valid && d < p.Dd) ? p.desc[row * p.Dd + d] : 0.0f;
+            xn2 = __fmaf_rn(x[d], x[d], xn2);
+            finite = finite && (fabsf(x[d]) <= 3.40282347e+38f);
+        }
+        const float cm2 = *p.cmax2;
+        // band = 2*(TF32 error of d~) + 2*(rounding error of the reference's float32 sum), generous constants:
+        //   |d~ - d| <= 2 * 2^-9 * 1.02 * ||x|| * max||c||      (two truncated operands per product, Cauchy-Schwarz)
+        //   reference sum: <= 40 * 2^-24 * (||x|| + max||c||)^2
+        const float xn = __fsqrt_rn(xn2), cmx = __fsqrt_rn(cm2);
+        const float band = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
+        float lv[TLIST]; int32_t lk[TLIST];
+#pragma unroll
+        for (int i = 0; i < TLIST; ++i) { lv[i] = INFINITY; lk[i] = 0x7fffffff; }
+        float thr = INFINITY;                              // admit d~ < thr = best + band (best = lv[0])
+        for (int t = 0; t < ntiles; ++t) {
+            const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
+            mbar_wait(&acc_full[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TILE_N);
+            const float* cn_t = p.cn + (int64_t)t * TILE_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+                float acc[32];
+                tmem_ld32(taddr + c0, acc);
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 cn4 = __ldg(reinterpret_cast<const float4*>(cn_t + c0 + j4));
+                    const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float dt = __fmaf_rn(-2.0f, acc[j4 + j], cnv[j]);
+                        if (dt < thr) {                     // rare: sorted insertion (ascending), then tighten thr
+                            float v = dt; int32_t kk = t * TILE_N + c0 + j4 + j;
+#pragma unroll
+                            for (int u = 0; u < TLIST; ++u) {
+                                const bool sw = v < lv[u];
+                                const float tv = sw ? lv[u] : v; const int32_t tk = sw ? lk[u] : kk;
+                                lv[u] = sw ? v : lv[u]; lk[u] = sw ? kk : lk[u];
+                                v = tv; kk = tk;
+                            }
+                            thr = lv[0] + band;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+        if (valid) {
+            int32_t cell = 0; bool resolved = true;
+            if (finite) {
+                // every list entry within the final band is a candidate; a full list may have lost candidates
+                const float lim = lv[0] + band;
+                if (lv[TLIST - 1] <= lim) resolved = false;
+                else {
+                    float best = INFINITY; int32_t bk = 0x7fffffff;
+#pragma unroll
+                    for (int u = 0; u < TLIST; ++u) {
+                        if (lv[u] <= lim && lk[u] < p.K) {
+                            const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)lk[u] * p.Dd, p.Dd);
+                            if (dex < best || (dex == best && lk[u] < bk)) { best = dex; bk = lk[u]; }
+                        }
+                    }
+                    if (bk == 0x7fffffff) resolved = false; else cell = bk;
+                }
+            }
+            // non-finite descriptor: every distance is inf or NaN -> first index (centroids are finite)
+            if (resolved) {
+                p.cells[row] = cell;
+                if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
+            } else {
+                const int slot = atomicAdd(p.fallback_count, 1);
+                p.fallback_rows[slot] = (int32_t)row;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// exact brute force for the (rare) rows the tensor pass could not resolve: one warp per listed row
+__global__ void __launch_bounds__(128) qdx_cells_tc_fallback_kernel(const QdxTcParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n = *p.fallback_count;
+    for (int64_t i = w; i < n; i += nw) {
+        const int64_t row = p.fallback_rows[i];
+        const float* x = p.desc + row * p.Dd;
+        float best = INFINITY; int64_t bk = 0x7fffffff;
+        for (int64_t k = lane; k < p.K; k += 32) {
+            const float* c = p.cent + k * p.Dd;
+            float acc = 0.0f;
+            for (int d = 0; d < p.Dd; ++d) { float df = x[d] - c[d]; float s = df * df; acc = d ? acc + s : s; }
+            if (acc < best) { best = acc; bk = k; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const long long ok = __shfl_xor_sync(0xffffffffu, (long long)bk, o);
+            if (ob < best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+        }
+        if (lane == 0) {
+            const int32_t cell = bk == 0x7fffffff ? 0 : (int32_t)bk;
+            p.cells[row] = cell;
+            if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
+        }
+    }
+}
+
+extern "C" {
+
+int qdx_cells_tc_workspace(int64_t K, int64_t B, int64_t* prep_floats, int64_t* scratch_ints) {
+    if (K <= 0 || B < 0 || !prep_floats || !scratch_ints) return QDX_ERR_ARG;
+    const int64_t Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
+    *prep_floats = Kpad * tc::KD + Kpad + 64;      // swizzled centroids | ||c||^2 | max ||c||^2 (+ padding)
+    *scratch_ints = B + 64;                         // fallback rows | counter
+    return 0;
+}
+
+int qdx_cells_tc_prepare(const float* centroids, int64_t K, int32_t desc_dim, float* prep, void* stream) {
+    if (!centroids || !prep || K <= 0 || desc_dim < 1 || desc_dim > tc::KD) return QDX_ERR_ARG;
+    const int64_t Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
+    float* cs = prep; float* cn = prep + Kpad * tc::KD; float* cmax2 = cn + Kpad;
+    cudaError_t e = cudaMemsetAsync(cmax2, 0, 64 * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    qdx_cells_tc_prepare_kernel<<<(unsigned)((Kpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, Kpad, cs, cn, cmax2);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const float* prep,
+                 int32_t* scratch, int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
+                 uint32_t idx_base, int32_t first_wins, void* stream) {
+    if (!desc || !centroids || !prep || !scratch || !out_cells || B < 0 || K <= 0 || desc_dim < 1 || desc_dim > tc::KD) return QDX_ERR_ARG;
+    if (offer && (!ws || !rep_fitness || !fitness)) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    QdxTcParams p;
+    p.desc = desc; p.B = B; p.Dd = desc_dim; p.cent = centroids; p.K = K;
+    p.Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
+    p.cs = prep; p.cn = prep + p.Kpad * tc::KD; p.cmax2 = p.cn + p.Kpad;
+    p.cells = out_cells; p.fallback_rows = scratch; p.fallback_count = scratch + B;
+    p.ws = ws; p.rep_f = rep_fitness; p.fit = fitness; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
+    cudaError_t e = cudaMemsetAsync(p.fallback_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(qdx_cells_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    qdx_cells_tc_kernel<<<(unsigned)((B + tc::TILE_M - 1) / tc::TILE_M), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p);
+    QDX_CHECK_LAUNCH();
+    qdx_cells_tc_fallback_kernel<<<148, 128, 0, st>>>(p);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

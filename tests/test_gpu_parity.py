@@ -212,6 +212,69 @@ def test_cells_bruteforce_cvt(dev, co, K, Dd, B):
     assert np.array_equal(got[:4096], qn.get_cells_indices(desc[:4096], cent))
 
 
+@pytest.mark.parametrize("K,Dd,B", [(5000, 32, 4096), (50000, 32, 8192), (2000, 16, 1000), (1024, 8, 300), (3333, 24, 129), (1500, 31, 777)])
+def test_cells_tensor_core_path(dev, co, K, Dd, B):
+    """tcgen05 TF32 pass + exact FP32 re-rank == brute-force argmin of the reference expression, bit for bit:
+    random points, exact duplicates of centroids (ties -> first index), midpoints of centroid pairs (near-ties
+    inside the TF32 error band), clustered centroids (candidate-list overflow -> exact fallback), NaN / inf rows."""
+    from qdax_b200 import _native
+
+    rng = np.random.default_rng(K * Dd)
+    cent = rng.random((K, Dd)).astype(np.float32)
+    cent[K // 3] = cent[K // 5]                                   # duplicated centroid
+    cent[100:140] = cent[99] + (rng.random((40, Dd)) * 1e-4).astype(np.float32)   # tight cluster: > TLIST candidates in band
+    desc = rng.random((B, Dd)).astype(np.float32)
+    desc[:16] = cent[K // 3]
+    desc[16:48] = ((cent[rng.integers(0, K, 32)].astype(np.float64) + cent[rng.integers(0, K, 32)]) / 2).astype(np.float32)
+    desc[48:64] = cent[99] + (rng.random((16, Dd)) * 1e-4).astype(np.float32)
+    desc[64, 0] = np.nan
+    desc[65, Dd - 1] = np.inf
+    desc[66] = 0.0
+    desc[67] = 1.0
+    desc[68:100] = cent[rng.integers(0, K, 32)] * np.float32(1.0000001)
+    got = N(_native.cells_tc(T(desc, dev), T(cent, dev)))
+    ref = co.cells(desc, cent)
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} of {B} rows differ, first at {np.nonzero(got != ref)[0][:5]}"
+    # through the public entry point (routes to the tensor-core path for 8 <= Dd <= 32, K >= 1024)
+    from qdax_b200.core.containers.mapelites_repertoire import get_cells_indices
+    assert np.array_equal(N(get_cells_indices(T(desc, dev), T(cent, dev))), ref)
+    # and with the offer fused: add() on a CVT repertoire
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+    D = 40
+    g = rng.random((B, D)).astype(np.float32)
+    f = np.round(rng.standard_normal(B), 1).astype(np.float32)
+    rep = MapElitesRepertoire.init_default(torch.zeros(D, device=dev), T(cent, dev))
+    new = rep.add(T(g, dev), T(desc, dev), T(f, dev))
+    G, F, Dn, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, Dd)), g, f, desc, ref)
+    assert np.array_equal(N(new.genotypes), G) and np.array_equal(N(new.fitnesses).ravel(), F) and np.array_equal(N(new.descriptors), Dn, equal_nan=True)
+
+
+def test_sphere_highdim_cvt_generation(dev, co):
+    """BASELINE config 4 shape at reduced size: sphere D=1000 (chunked generate), desc = p[:32], CVT-like centroids
+    (tensor-core cell assignment), full generations vs the oracle."""
+    from qdax_b200 import lax as qlax
+    from qdax_b200 import random as qr
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+    from qdax_b200.core.map_elites import MAPElites
+    from qdax_b200.tasks.standard_functions import sphere_scoring_function
+    from qdax_b200.utils.metrics import default_qd_metrics
+
+    K, D, B, Dd = 2048, 1000, 1024, 32
+    cent = np.random.default_rng(1).random((K, Dd)).astype(np.float32)
+    init = N(qr.uniform(jr.key(1), (64, D), device=dev))
+    em = MixingEmitter(lambda x, y: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B)
+    me = MAPElites(functools.partial(sphere_scoring_function, desc_dim=Dd), em, functools.partial(default_qd_metrics, qd_offset=0.0))
+    rep, state, _ = me.init(T(init, dev), T(cent, dev), jr.key(2))
+    assert me._fused_config(rep) is not None
+    f0, d0 = co.score("sphere", init, Dd)
+    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, Dd)), init, f0, d0, co.cells(d0, cent))
+    assert np.array_equal(N(rep.genotypes), g)
+    (rep2, _, key2), metrics = qlax.scan(me.scan_update, (rep, state, jr.key(3)), (), length=3)
+    G, F, Dn, k2, M, _ = co.map_elites_scan(g, f, d, cent, jr.key(3), 3, B, "sphere")
+    assert np.array_equal(N(rep2.fitnesses).ravel(), F) and np.array_equal(N(rep2.genotypes), G) and (np.array(key2) == k2).all()
+
+
 # ------------------------------------------------------------------------------------------------- insertion
 def test_reference_add_kat(dev):
     # /root/reference/tests/core_test/containers_test/mapelites_repertoire_test.py:11-81
