@@ -4,13 +4,16 @@
 // /root/reference): argmin_k sum_d (x_d - c_kd)^2 in float32, sequential over d, FIRST minimum.  The reference
 // never expands the square; neither does the final decision here:
 //
-//   1. tensor pass   d~(i,k) = ||c_k||^2 - 2 x_i . c_k   with x . c from tcgen05.mma kind::tf32 (M=128, N=256, K=32:
+//   1. tensor pass   d~(i,k) = ||c_k||^2 - 2 x_i . c_k   with x . c from tcgen05.mma kind::tf32 (M=128, N=128, K=32:
 //                    four K=8 steps), FP32 accumulators in TMEM, double buffered; centroid tiles stream through a
-//                    3-stage shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier
+//                    4-stage shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier
 //                    complete_tx) from a copy of the centroids that was written ONCE in the 128-byte-swizzled
 //                    K-major layout the UMMA descriptors expect (a 32-float row is exactly one swizzle row, so no
 //                    tensor map is needed); warp roles: 1 copy-issuer, 1 MMA-issuer, 4 epilogue warps (one TMEM
 //                    lane quadrant each, thread = descriptor row).
+//                    Both x and c are centred on the centroid mean mu first (distances are translation invariant):
+//                    the TF32 error scales with ||x - mu|| * ||c - mu||, 4x smaller than the uncentred product for
+//                    data in [0,1]^32, and it makes the bound usable for tessellations far from the origin.
 //   2. candidates    every k with d~ <= min_k d~ + band_i is kept (sorted list of T), where band_i bounds twice the
 //                    TF32 error (|x~c~ - xc| <= 2^-9 |xc| per product, Cauchy-Schwarz over the row) plus twice the
 //                    rounding error of the reference's own float32 sum -- so the list provably contains every index
@@ -29,12 +32,13 @@ namespace tc {
 
 constexpr int KD = 32;                 // padded descriptor dimension = one 128-byte swizzle row of float32
 constexpr int TILE_M = 128;            // descriptor rows per CTA (UMMA M)
-constexpr int TILE_N = 256;            // centroids per MMA (UMMA N)
-constexpr int STAGES = 3;              // shared-memory ring of centroid tiles
-constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (2 x 256 columns = all 512)
-constexpr int TLIST = 8;               // candidates kept per row
+constexpr int TILE_N = 128;            // centroids per MMA (UMMA N); 2 x 128 TMEM columns per CTA -> two CTAs per SM
+constexpr int STAGES = 4;              // shared-memory ring of centroid tiles
+constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (2 x 128 columns)
+constexpr int TMEM_COLS = ACC_STAGES * TILE_N;
+constexpr int TLIST = 16;              // candidates kept per row
 constexpr int A_BYTES = TILE_M * KD * 4;        // 16 KB
-constexpr int B_BYTES = TILE_N * KD * 4;        // 32 KB
+constexpr int B_BYTES = TILE_N * KD * 4;        // 16 KB
 constexpr int NUM_THREADS = 192;       // warp 0: copies, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/;
 
@@ -86,21 +90,29 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread t of the warp <-> TMEM lane base + t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread t of the warp <-> TMEM lane base + t).
+// The load is asynchronous: v[] must not be read before tmem_wait_ld(v), which carries v as in/out operands so that
+// neither the compiler nor ptxas can hoist a consumer above the wait.
+#define QDX_V32(C) C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) \
+                   C(16) C(17) C(18) C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+          "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+          "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+          "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]),
+          "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]),
+          "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+        :: "memory");
 }
 
 // Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row atoms 1024 bytes apart.
@@ -124,8 +136,21 @@ __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c
 // ---------------------------------------------------------------------------------------------------------------
 // one-off per tessellation: swizzled, zero-padded copy of the centroids + ||c||^2 (+inf for padding) + max ||c||
 // ---------------------------------------------------------------------------------------------------------------
+// column means of the centroids (deterministic: one CTA per dimension, fixed-shape tree)
+__global__ void __launch_bounds__(256) qdx_cells_tc_mean_kernel(const float* __restrict__ cent, int64_t K, int32_t Dd, float* __restrict__ mu) {
+    __shared__ double s_part[256];
+    const int d = blockIdx.x;
+    double acc = 0.0;
+    if (d < Dd) for (int64_t k = threadIdx.x; k < K; k += blockDim.x) acc += (double)cent[k * Dd + d];
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) mu[d] = d < Dd ? (float)(s_part[0] / (double)K) : 0.0f;
+}
+
 __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* __restrict__ cent, int64_t K, int32_t Dd,
-                                                                   int64_t Kpad, float* __restrict__ cs, float* __restrict__ cn,
+                                                                   int64_t Kpad, const float* __restrict__ mu,
+                                                                   float* __restrict__ cs, float* __restrict__ cn,
                                                                    float* __restrict__ cmax2) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kpad) return;
@@ -133,7 +158,7 @@ __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* 
     float n2 = 0.0f;
 #pragma unroll
     for (int d = 0; d < tc::KD; ++d) {
-        row[d] = (k < K && d < Dd) ? cent[k * Dd + d] : 0.0f;
+        row[d] = (k < K && d < Dd) ? cent[k * Dd + d] - mu[d] : 0.0f;
         n2 = __fmaf_rn(row[d], row[d], n2);
     }
     const int64_t tile = k / tc::TILE_N;
@@ -152,7 +177,7 @@ __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* 
 struct QdxTcParams {
     const float* desc; int64_t B; int32_t Dd;
     const float* cent; int64_t K; int64_t Kpad;
-    const float* cs; const float* cn; const float* cmax2;
+    const float* cs; const float* cn; const float* cmax2; const float* mu;   // cmax2[0] = max ||c-mu||^2, mu = cmax2 + 32
     int32_t* cells; int32_t* fallback_rows; int32_t* fallback_count;
     void* ws; const float* rep_f; const float* fit; int32_t offer; uint32_t idx_base; int32_t first_wins;
 };
@@ -168,7 +193,7 @@ __device__ __forceinline__ float qdx_exact_dist(const float (&x)[DDPAD], const f
     return acc;
 }
 
-__global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const QdxTcParams p) {
+__global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const QdxTcParams p) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-byte alignment
@@ -190,14 +215,14 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const 
         for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }   // 4 epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_base_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
     // A tile: 128 descriptor rows, zero-padded to 32 floats, written in the swizzled layout by all threads
     for (int i = threadIdx.x; i < TILE_M * 8; i += NUM_THREADS) {
         const int r = i >> 3, c = i & 7;
         const int64_t row = row0 + r;
         float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int d = 4 * c + j; v[j] = (row < p.B && d < p.Dd) ? p.desc[row * p.Dd + d] : 0.0f; }
+        for (int j = 0; j < 4; ++j) { const int d = 4 * c + j; v[j] = (row < p.B && d < p.Dd) ? p.desc[row * p.Dd + d] - p.mu[d] : 0.0f; }
         *reinterpret_cast<float4*>(sA + sw128_offset(r, c)) = make_float4(v[0], v[1], v[2], v[3]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA (async proxy)
@@ -240,54 +265,92 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const 
         const int r = quad * 32 + lane;
         const int64_t row = row0 + r;
         const bool valid = row < p.B;
-        float x[KD];
-        float xn2 = 0.0f; bool finite = true;
+        float xn2 = 0.0f, xo2 = 0.0f, mu2 = 0.0f; bool finite = true;
 #pragma unroll
         for (int d = 0; d < KD; ++d) {
-            x[d] = (valid && d < p.Dd) ? p.desc[row * p.Dd + d] : 0.0f;
-            xn2 = __fmaf_rn(x[d], x[d], xn2);
-            finite = finite && (fabsf(x[d]) <= 3.40282347e+38f);
+            const float xd = (valid && d < p.Dd) ? p.desc[row * p.Dd + d] : 0.0f;
+            const float m = d < p.Dd ? p.mu[d] : 0.0f;
+            const float xc = xd - m;
+            xn2 = __fmaf_rn(xc, xc, xn2); xo2 = __fmaf_rn(xd, xd, xo2); mu2 = __fmaf_rn(m, m, mu2);
+            finite = finite && (fabsf(xd) <= 3.40282347e+38f);
         }
         const float cm2 = *p.cmax2;
-        // band = 2*(TF32 error of d~) + 2*(rounding error of the reference's float32 sum), generous constants:
-        //   |d~ - d| <= 2 * 2^-9 * 1.02 * ||x|| * max||c||      (two truncated operands per product, Cauchy-Schwarz)
-        //   reference sum: <= 40 * 2^-24 * (||x|| + max||c||)^2
+        // band = 2*(error of d~ against the exact centred distance) + 2*(rounding error of the reference's float32 sum):
+        //   TF32:       |d~ - d| <= 2 * 2^-9 * 1.02 * ||x-mu|| * max||c-mu||   (two truncated operands per product, Cauchy-Schwarz)
+        //   centring:   fl(x-mu), fl(c-mu) are off by <= 2^-24 (|x|+|mu|) per component -> <= 2^-19 (||x||+||mu||+1)(max||c-mu||+||x-mu||+1)
+        //   reference:  <= 40 * 2^-24 * (||x-mu|| + max||c-mu||)^2
         const float xn = __fsqrt_rn(xn2), cmx = __fsqrt_rn(cm2);
-        const float band = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
+        const float band = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-18f * (__fsqrt_rn(xo2) + __fsqrt_rn(mu2) + 1.0f) * (cmx + xn + 1.0f)
+                         + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
         float lv[TLIST]; int32_t lk[TLIST];
 #pragma unroll
         for (int i = 0; i < TLIST; ++i) { lv[i] = INFINITY; lk[i] = 0x7fffffff; }
         float thr = INFINITY;                              // admit d~ < thr = best + band (best = lv[0])
+
+        // one 32-column chunk: d~ in place, branch-free running minimum; the (rare) admissible columns are then
+        // visited through a bit mask so the sorted insertion exists once in the instruction stream
+        auto process = [&](float (&acc)[32], const float4 (&cn)[8], int kbase) {
+            float m = INFINITY;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float cnv[4] = {cn[q].x, cn[q].y, cn[q].z, cn[q].w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    acc[4 * q + jj] = __fmaf_rn(-2.0f, acc[4 * q + jj], cnv[jj]);
+                    m = fminf(m, acc[4 * q + jj]);
+                }
+            }
+            if (m < thr) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int jx = 0; jx < 32; ++jx) mask |= (acc[jx] < thr ? 1u : 0u) << jx;
+                while (mask) {
+                    const int jx = __ffs(mask) - 1; mask &= mask - 1;
+                    float v = acc[0];
+#pragma unroll
+                    for (int u = 1; u < 32; ++u) v = (jx == u) ? acc[u] : v;
+                    if (v < thr) {                          // thr may have tightened since the mask was built
+                        int32_t kk = kbase + jx;
+#pragma unroll
+                        for (int u = 0; u < TLIST; ++u) {   // sorted insertion, ascending
+                            const bool sw = v < lv[u];
+                            const float tv = sw ? lv[u] : v; const int32_t tk = sw ? lk[u] : kk;
+                            lv[u] = sw ? v : lv[u]; lk[u] = sw ? kk : lk[u];
+                            v = tv; kk = tk;
+                        }
+                        thr = lv[0] + band;
+                    }
+                }
+            }
+        };
+        auto load_cn = [&](float4 (&cn)[8], int64_t col) {  // same addresses for every lane / epilogue warp: L1-resident
+            if (col >= p.Kpad) col = 0;
+            const float4* src = reinterpret_cast<const float4*>(p.cn + col);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cn[q] = __ldg(src + q);
+        };
+
+        // software pipeline over 32-column chunks (4 per tile, processed in ping-pong pairs): the TMEM load and the
+        // ||c-mu||^2 fetch of chunk i+1 are in flight while chunk i is processed
+        float accA[32], accB[32]; float4 cnA[8], cnB[8];
+        load_cn(cnA, 0);
         for (int t = 0; t < ntiles; ++t) {
             const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
             mbar_wait(&acc_full[a], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TILE_N);
-            const float* cn_t = p.cn + (int64_t)t * TILE_N;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TILE_N; c0 += 32) {
-                float acc[32];
-                tmem_ld32(taddr + c0, acc);
+            const int kt = t * TILE_N;
+            tmem_ld32(taddr, accA);
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const float4 cn4 = __ldg(reinterpret_cast<const float4*>(cn_t + c0 + j4));
-                    const float cnv[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float dt = __fmaf_rn(-2.0f, acc[j4 + j], cnv[j]);
-                        if (dt < thr) {                     // rare: sorted insertion (ascending), then tighten thr
-                            float v = dt; int32_t kk = t * TILE_N + c0 + j4 + j;
-#pragma unroll
-                            for (int u = 0; u < TLIST; ++u) {
-                                const bool sw = v < lv[u];
-                                const float tv = sw ? lv[u] : v; const int32_t tk = sw ? lk[u] : kk;
-                                lv[u] = sw ? v : lv[u]; lk[u] = sw ? kk : lk[u];
-                                v = tv; kk = tk;
-                            }
-                            thr = lv[0] + band;
-                        }
-                    }
-                }
+            for (int c0 = 0; c0 < TILE_N; c0 += 64) {
+                tmem_wait_ld(accA);                                    // accA (chunk c0) has landed
+                tmem_ld32(taddr + c0 + 32, accB);                      // chunk c0+32 in flight
+                load_cn(cnB, (int64_t)kt + c0 + 32);
+                process(accA, cnA, kt + c0);
+                tmem_wait_ld(accB);                                    // accB has landed
+                if (c0 + 64 < TILE_N) tmem_ld32(taddr + c0 + 64, accA);
+                load_cn(cnA, (int64_t)kt + c0 + 64);                   // (first chunk of the next tile when c0 + 64 == TILE_N)
+                process(accB, cnB, kt + c0 + 32);
             }
             tc_fence_before();
             __syncwarp();
@@ -300,12 +363,18 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const 
                 const float lim = lv[0] + band;
                 if (lv[TLIST - 1] <= lim) resolved = false;
                 else {
-                    float best = INFINITY; int32_t bk = 0x7fffffff;
+                    float x[KD];
 #pragma unroll
+                    for (int d = 0; d < KD; ++d) x[d] = d < p.Dd ? p.desc[row * p.Dd + d] : 0.0f;
+                    float best = INFINITY; int32_t bk = 0x7fffffff;
+#pragma unroll 1
                     for (int u = 0; u < TLIST; ++u) {
-                        if (lv[u] <= lim && lk[u] < p.K) {
-                            const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)lk[u] * p.Dd, p.Dd);
-                            if (dex < best || (dex == best && lk[u] < bk)) { best = dex; bk = lk[u]; }
+                        float lvu = lv[0]; int32_t lku = lk[0];
+#pragma unroll
+                        for (int w2 = 1; w2 < TLIST; ++w2) { lvu = (u == w2) ? lv[w2] : lvu; lku = (u == w2) ? lk[w2] : lku; }
+                        if (lvu <= lim && lku < p.K) {
+                            const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)lku * p.Dd, p.Dd);
+                            if (dex < best || (dex == best && lku < bk)) { best = dex; bk = lku; }
                         }
                     }
                     if (bk == 0x7fffffff) resolved = false; else cell = bk;
@@ -323,7 +392,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) qdx_cells_tc_kernel(const 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // exact brute force for the (rare) rows the tensor pass could not resolve: one warp per listed row
@@ -360,7 +429,7 @@ extern "C" {
 int qdx_cells_tc_workspace(int64_t K, int64_t B, int64_t* prep_floats, int64_t* scratch_ints) {
     if (K <= 0 || B < 0 || !prep_floats || !scratch_ints) return QDX_ERR_ARG;
     const int64_t Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
-    *prep_floats = Kpad * tc::KD + Kpad + 64;      // swizzled centroids | ||c||^2 | max ||c||^2 (+ padding)
+    *prep_floats = Kpad * tc::KD + Kpad + 64;      // swizzled centred centroids | ||c-mu||^2 | [max ||c-mu||^2, pad x31, mu x32]
     *scratch_ints = B + 64;                         // fallback rows | counter
     return 0;
 }
@@ -371,7 +440,10 @@ int qdx_cells_tc_prepare(const float* centroids, int64_t K, int32_t desc_dim, fl
     float* cs = prep; float* cn = prep + Kpad * tc::KD; float* cmax2 = cn + Kpad;
     cudaError_t e = cudaMemsetAsync(cmax2, 0, 64 * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
-    qdx_cells_tc_prepare_kernel<<<(unsigned)((Kpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, Kpad, cs, cn, cmax2);
+    float* mu = cmax2 + 32;
+    qdx_cells_tc_mean_kernel<<<tc::KD, 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, mu);
+    QDX_CHECK_LAUNCH();
+    qdx_cells_tc_prepare_kernel<<<(unsigned)((Kpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, Kpad, mu, cs, cn, cmax2);
     QDX_CHECK_LAUNCH();
     return 0;
 }
@@ -387,7 +459,7 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
     QdxTcParams p;
     p.desc = desc; p.B = B; p.Dd = desc_dim; p.cent = centroids; p.K = K;
     p.Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
-    p.cs = prep; p.cn = prep + p.Kpad * tc::KD; p.cmax2 = p.cn + p.Kpad;
+    p.cs = prep; p.cn = prep + p.Kpad * tc::KD; p.cmax2 = p.cn + p.Kpad; p.mu = p.cmax2 + 32;
     p.cells = out_cells; p.fallback_rows = scratch; p.fallback_count = scratch + B;
     p.ws = ws; p.rep_f = rep_fitness; p.fit = fitness; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
     cudaError_t e = cudaMemsetAsync(p.fallback_count, 0, sizeof(int32_t), st);
