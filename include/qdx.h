@@ -122,6 +122,13 @@ int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, 
 int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,
                           float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval, float* out,
                           void* stream);
+/* polynomial_mutation (mutation_operators.py:81-117; n_mutate = int(proportion_to_mutate * D), eta_plus_1 = 1 + eta,
+ * mutpow = 1 / (1 + eta)) and polynomial_crossover (:139-172; n_change = int(proportion_var_to_change * D)).
+ * out must not alias the inputs. */
+int qdx_polynomial_mutation(const float* x, int64_t B, int64_t D, uint32_t k0, uint32_t k1, int32_t n_mutate, float eta_plus_1,
+                            float mutpow, float minval, float maxval, float* out, void* stream);
+int qdx_polynomial_crossover(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, int32_t n_change,
+                             float* out, void* stream);
 /* jax.random streams: kind 0 bits (uint32), 1 uniform(minval, maxval), 2 normal */
 int qdx_random(uint32_t k0, uint32_t k1, int64_t n, int32_t kind, float minval, float maxval, void* out, void* stream);
 /* default_qd_metrics -> {qd_score, max_fitness, coverage} */

@@ -99,6 +99,31 @@ def math_probe(which: int, x) -> np.ndarray:
     return out
 
 
+def math_probe2(which: int, x, aux: float = 0.0) -> np.ndarray:
+    x = _f(x)
+    out = np.zeros_like(x)
+    _chk(lib().qo_math_probe2(C.c_int(which), C.c_int64(x.size), _p(x), C.c_float(aux), _p(out)), "math_probe2")
+    return out
+
+
+def polynomial_mutation(x, key, proportion_to_mutate, eta, minval, maxval) -> np.ndarray:
+    x = _f(x)
+    B, D = x.shape
+    out = np.zeros_like(x)
+    _chk(lib().qo_polynomial_mutation(_p(x), C.c_int64(B), C.c_int64(D), _p(_key(key)), C.c_float(proportion_to_mutate), C.c_float(eta),
+                                      C.c_float(minval), C.c_float(maxval), _p(out)), "polynomial_mutation")
+    return out
+
+
+def polynomial_crossover(x1, x2, key, proportion_var_to_change) -> np.ndarray:
+    x1, x2 = _f(x1), _f(x2)
+    B, D = x1.shape
+    out = np.zeros_like(x1)
+    _chk(lib().qo_polynomial_crossover(_p(x1), _p(x2), C.c_int64(B), C.c_int64(D), _p(_key(key)), C.c_float(proportion_var_to_change), _p(out)),
+         "polynomial_crossover")
+    return out
+
+
 def select_indices(fitnesses, key, num: int) -> np.ndarray:
     f = _f(fitnesses).reshape(-1)
     out = np.zeros(num, dtype=np.int32)

@@ -144,6 +144,38 @@ static inline float spec_erfinvf(float x) {
     if (fabsf(x) == 1.0f) return x * 3.40282347e+38f;
     return p * x;
 }
+/* exp(z): n = rint(z*log2e), r = z - n*ln2 (two-term, fused), degree-6 polynomial, scale by 2^n (two steps so that
+ * results down to the subnormal range and up to FLT_MAX are produced by plain multiplications). */
+static inline float spec_expf(float z) {
+    if (z != z) return z;
+    if (z > 88.75f) return INFINITY;
+    if (z < -104.0f) return 0.0f;
+    float n = rintf(z * 0x1.715476p+0f);
+    float r = fmaf(n, -0x1.62e400p-1f, z);
+    r = fmaf(n, -0x1.7f7d1cp-20f, r);
+    float p = 0x1.6c16c2p-10f;                 /* 1/720 */
+    p = fmaf(p, r, 0x1.111112p-7f);            /* 1/120 */
+    p = fmaf(p, r, 0x1.555556p-5f);            /* 1/24  */
+    p = fmaf(p, r, 0x1.555556p-3f);            /* 1/6   */
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    int ni = (int)n;
+    int h = ni / 2;
+    float s1 = u2f((uint32_t)(h + 127) << 23), s2 = u2f((uint32_t)(ni - h + 127) << 23);
+    return (p * s1) * s2;
+}
+/* pow(x, y) for the polynomial mutation (x >= 0 expected): exp(y * log(x)); pow(0, y > 0) = 0; x < 0 -> NaN. */
+static inline float spec_powf(float x, float y) {
+    if (x != x || y != y) return NAN;
+    if (x < 0.0f) return NAN;
+    if (x == 0.0f) return y > 0.0f ? 0.0f : (y == 0.0f ? 1.0f : INFINITY);
+    if (x == INFINITY) return y > 0.0f ? INFINITY : (y == 0.0f ? 1.0f : 0.0f);
+    float lg;
+    if (x < 0x1p-126f) lg = spec_logf(x * 0x1p+25f) - 0x1.154246p+4f;   /* subnormal: log(x 2^25) - 25 ln 2 */
+    else lg = spec_logf(x);
+    return spec_expf(y * lg);
+}
 /* jax.random.normal from one 32-bit draw: sqrt(2) * erfinv(max(lo, f*2 + lo)), lo = nextafter(-1, 0). */
 static inline float normal_from_bits(uint32_t bits) {
     const float lo = -0x1.fffffep-1f;
@@ -286,6 +318,100 @@ QO_API int qo_isoline_variation(const float* x1, const float* x2, int64_t B, int
     isoline(x1, x2, NULL, NULL, B, D, k, iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
     return 0;
 }
+/* ------------------------------------------------------------------ polynomial mutation / crossover
+ * qdax/core/emitters/mutation_operators.py:12-117 and :120-172.  keys = split(key, B); per row:
+ *   key, sub = split(key_r); positions = choice(sub, arange(D), (n,), replace=False) = permutation(sub, D)[:n]
+ *   (permutation: `rounds` passes of  k, s = split(k); stable sort of the array by random_bits(s, (D,)) )
+ *   key, sub = split(key); rand = uniform(sub, (n,)); polynomial delta; x[positions] += delta * (hi - lo); clip. */
+static int perm_rounds(int64_t n) {
+    if (n <= 1) return 1;
+    return (int)ceil(3.0 * log((double)n) / log(4294967295.0));
+}
+typedef struct { uint32_t key; int32_t pos; int32_t val; } qo_pk;
+static int pk_cmp(const void* a, const void* b) {
+    const qo_pk* x = (const qo_pk*)a; const qo_pk* y = (const qo_pk*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos ? 1 : 0);       /* stable */
+}
+static void permutation(qo_key key, int64_t n, int32_t* out, qo_pk* tmp) {
+    for (int64_t i = 0; i < n; ++i) out[i] = (int32_t)i;
+    int rounds = perm_rounds(n);
+    for (int r = 0; r < rounds; ++r) {
+        qo_key sub = split_i(key, 1); key = split_i(key, 0);
+        for (int64_t i = 0; i < n; ++i) { tmp[i].key = bits32(sub, (uint64_t)i); tmp[i].pos = (int32_t)i; tmp[i].val = out[i]; }
+        qsort(tmp, (size_t)n, sizeof(qo_pk), pk_cmp);
+        for (int64_t i = 0; i < n; ++i) out[i] = tmp[i].val;
+    }
+}
+QO_API int qo_polynomial_mutation(const float* x, int64_t B, int64_t D, const uint32_t* key, float proportion, float eta,
+                                  float minv, float maxv, float* out) {
+    qo_key k = {key[0], key[1]};
+    const int64_t n = (int64_t)((double)proportion * (double)D);     /* int(proportion_to_mutate * num_positions)  :40 */
+    const float rng = maxv - minv, mutpow = (float)(1.0 / (1.0 + (double)eta)), ep1 = (float)(1.0 + (double)eta);
+    int rc = 0;
+#pragma omp parallel
+    {
+        int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)D);
+        qo_pk* tmp = (qo_pk*)malloc(sizeof(qo_pk) * (size_t)D);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < B; ++i) {
+            if (!perm || !tmp) { rc = -2; continue; }
+            qo_key kr = split_i(k, (uint64_t)i);                    /* :107 */
+            qo_key sub1 = split_i(kr, 1), k1 = split_i(kr, 0);      /* :41 */
+            permutation(sub1, D, perm, tmp);                        /* :42-45 */
+            qo_key sub2 = split_i(k1, 1);                           /* :53 */
+            float* o = out + i * D;
+            for (int64_t d = 0; d < D; ++d) o[d] = x[i * D + d];
+            for (int64_t j = 0; j < n; ++j) {
+                const int32_t pos = perm[j];
+                const float mx = x[i * D + pos];
+                const float d1 = (mx - minv) / rng, d2 = (maxv - mx) / rng;
+                const float r = unit_float(bits32(sub2, (uint64_t)j));              /* :54-60 */
+                float v1 = 2.0f * r + spec_powf(d1, ep1) * (1.0f - 2.0f * r);         /* :62 */
+                float v2 = 2.0f * (1.0f - r) + 2.0f * (spec_powf(d2, ep1) * (r - 0.5f));   /* :63 */
+                v1 = spec_powf(v1, mutpow) - 1.0f;                                  /* :64 */
+                v2 = 1.0f - spec_powf(v2, mutpow);                                  /* :65 */
+                const float dq = r < 0.5f ? v1 : v2;                                /* :67-69 */
+                o[pos] = mx + dq * rng;                                             /* :72 */
+            }
+            for (int64_t d = 0; d < D; ++d) o[d] = min_nanprop(max_nanprop(o[d], minv), maxv);   /* :75 */
+        }
+        free(perm); free(tmp);
+    }
+    return rc;
+}
+/* jax.random.randint(key, (n,), 0, span): two 32-bit draws per element from split(key), combined modulo span in uint32 */
+static inline uint32_t randint_one(qo_key k1, qo_key k2, uint64_t j, uint32_t span) {
+    uint32_t hi = bits32(k1, j), lo = bits32(k2, j);
+    uint32_t mult = (65536u % span); mult = (mult * mult) % span;
+    return ((hi % span) * mult + (lo % span)) % span;
+}
+QO_API int qo_polynomial_crossover(const float* x1, const float* x2, int64_t B, int64_t D, const uint32_t* key, float proportion,
+                                   float* out) {
+    qo_key k = {key[0], key[1]};
+    const int64_t n = (int64_t)((double)proportion * (double)D);     /* :130 */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < B; ++i) {
+        qo_key kr = split_i(k, (uint64_t)i);                        /* :164 */
+        qo_key r1 = split_i(kr, 0), r2 = split_i(kr, 1);            /* randint: k1, k2 = split(key) */
+        for (int64_t d = 0; d < D; ++d) out[i * D + d] = x1[i * D + d];
+        for (int64_t j = 0; j < n; ++j) {
+            uint32_t idx = randint_one(r1, r2, (uint64_t)j, (uint32_t)D);           /* :132 */
+            out[i * D + idx] = x2[i * D + idx];                                      /* :133 */
+        }
+    }
+    return 0;
+}
+/* which: 4 exp, 5 pow(in, aux) */
+QO_API int qo_math_probe2(int which, int64_t n, const float* in, float aux, float* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (which == 4) out[i] = spec_expf(in[i]);
+        else if (which == 5) out[i] = spec_powf(in[i], aux);
+        else return -1;
+    }
+    return 0;
+}
+
 /* MixingEmitter.emit with variation_percentage = 1 -- standard_emitters.py:51-62 */
 QO_API int qo_emit_isoline(const float* rep_g, const float* rep_f, int64_t K, int64_t D, const uint32_t* key, int64_t B,
                            float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "qdx_select_indices": [_vp, _u32, _u32, _i64, _vp, _vp],
     "qdx_gather_rows": [_vp, _vp, _i64, _i64, _vp, _vp],
     "qdx_isoline_variation": [_vp, _vp, _i64, _i64, _u32, _u32, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp],
+    "qdx_polynomial_mutation": [_vp, _i64, _i64, _u32, _u32, _i32, _f32, _f32, _f32, _f32, _vp, _vp],
+    "qdx_polynomial_crossover": [_vp, _vp, _i64, _i64, _u32, _u32, _i32, _vp, _vp],
     "qdx_random": [_u32, _u32, _i64, _i32, _f32, _f32, _vp, _vp],
     "qdx_metrics": [_vp, _i64, _f32, _vp, _vp],
     "qdx_dns_add": [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -93,7 +95,7 @@ def lib() -> C.CDLL:
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
 KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
-                   "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1,
+                   "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0
 

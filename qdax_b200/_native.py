@@ -277,6 +277,30 @@ def isoline_variation(x1, x2, key, iso_sigma, line_sigma, minval=None, maxval=No
     return out
 
 
+def polynomial_mutation(x, key, proportion_to_mutate: float, eta: float, minval: float, maxval: float) -> torch.Tensor:
+    x = require_cuda(x, "x")
+    B = x.shape[0]
+    D = x.numel() // max(B, 1)
+    k0, k1 = key_words(key)
+    out = torch.empty_like(x)
+    call("qdx_polynomial_mutation", _ptr(x), C.c_int64(B), C.c_int64(D), C.c_uint32(k0), C.c_uint32(k1),
+         C.c_int32(int(proportion_to_mutate * D)), C.c_float(1.0 + eta), C.c_float(1.0 / (1.0 + eta)), C.c_float(minval),
+         C.c_float(maxval), _ptr(out), _stream())
+    return out
+
+
+def polynomial_crossover(x1, x2, key, proportion_var_to_change: float) -> torch.Tensor:
+    x1 = require_cuda(x1, "x1")
+    x2 = require_cuda(x2, "x2")
+    B = x1.shape[0]
+    D = x1.numel() // max(B, 1)
+    k0, k1 = key_words(key)
+    out = torch.empty_like(x1)
+    call("qdx_polynomial_crossover", _ptr(x1), _ptr(x2), C.c_int64(B), C.c_int64(D), C.c_uint32(k0), C.c_uint32(k1),
+         C.c_int32(int(proportion_var_to_change * D)), _ptr(out), _stream())
+    return out
+
+
 def random_stream(key, n: int, kind: int, device, minval: float = 0.0, maxval: float = 1.0) -> torch.Tensor:
     k0, k1 = key_words(key)
     out = torch.empty(n, dtype=torch.float32 if kind else torch.int32, device=device)

@@ -1,8 +1,7 @@
 """Variation operators -- mirrors qdax/core/emitters/mutation_operators.py of the reference.
 
-isoline_variation (:175-226) runs as a hand-written kernel (Threefry-2x32 counter-based normal draws, one
-32-bit draw per gene, exactly jax.random.normal's stream).  polynomial_mutation / polynomial_crossover
-(:81-172) are SURVEY.md section 8(f) "next" rows and are not built yet."""
+isoline_variation (:175-226), polynomial_mutation (:81-117) and polynomial_crossover (:139-172) run as hand-written
+kernels driven by the exact jax.random streams (Threefry-2x32, counter-based)."""
 
 from __future__ import annotations
 
@@ -22,9 +21,18 @@ def isoline_variation(x1: torch.Tensor, x2: torch.Tensor, key, iso_sigma: float,
     return _native.isoline_variation(x1, x2, key, float(iso_sigma), float(line_sigma), minval, maxval)
 
 
-def polynomial_mutation(x, key, proportion_to_mutate: float, eta: float, minval: float, maxval: float):
-    raise NotImplementedError("polynomial_mutation (reference :81-117) is a SURVEY 8(f) 'next' row, not built in round 1")
+def polynomial_mutation(x: torch.Tensor, key, proportion_to_mutate: float, eta: float, minval: float, maxval: float) -> torch.Tensor:
+    """Polynomial mutation over a batch of genotypes (reference :81-117 / :12-78): per row, `int(proportion * D)` genes
+    chosen without replacement (jax.random.choice = first entries of a random permutation) receive the polynomial
+    perturbation driven by one uniform draw each; the row is clipped to [minval, maxval]."""
+    if isinstance(x, (dict, list, tuple)):
+        raise NotImplementedError("pytree genotypes are a SURVEY 8(f) 'next' row; pass a single (batch, D) tensor")
+    return _native.polynomial_mutation(x, key, float(proportion_to_mutate), float(eta), float(minval), float(maxval))
 
 
-def polynomial_crossover(x1, x2, key, proportion_var_to_change: float):
-    raise NotImplementedError("polynomial_crossover (reference :139-172) is a SURVEY 8(f) 'next' row, not built in round 1")
+def polynomial_crossover(x1: torch.Tensor, x2: torch.Tensor, key, proportion_var_to_change: float) -> torch.Tensor:
+    """Crossover over pairs of genotypes (reference :139-172 / :120-136): per row, `int(proportion * D)` positions drawn
+    WITH replacement (jax.random.randint) are copied from x2 into x1."""
+    if isinstance(x1, (dict, list, tuple)):
+        raise NotImplementedError("pytree genotypes are a SURVEY 8(f) 'next' row; pass a single (batch, D) tensor")
+    return _native.polynomial_crossover(x1, x2, key, float(proportion_var_to_change))

@@ -152,6 +152,38 @@ QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
     s_out = sv; c_out = cv;
 }
 
+// exp(z): n = rint(z*log2e), two-term fused reduction by ln2, degree-6 polynomial, two-step scaling by 2^n
+QDX_DEV float qdx_expf(float z) {
+    if (z != z) return z;
+    if (z > 88.75f) return INFINITY;
+    if (z < -104.0f) return 0.0f;
+    float n = rintf(z * 0x1.715476p+0f);
+    float r = __fmaf_rn(n, -0x1.62e400p-1f, z);
+    r = __fmaf_rn(n, -0x1.7f7d1cp-20f, r);
+    float p = 0x1.6c16c2p-10f;
+    p = __fmaf_rn(p, r, 0x1.111112p-7f);
+    p = __fmaf_rn(p, r, 0x1.555556p-5f);
+    p = __fmaf_rn(p, r, 0x1.555556p-3f);
+    p = __fmaf_rn(p, r, 0.5f);
+    p = __fmaf_rn(p, r, 1.0f);
+    p = __fmaf_rn(p, r, 1.0f);
+    int ni = (int)n;
+    int h = ni / 2;
+    float s1 = __uint_as_float((uint32_t)(h + 127) << 23), s2 = __uint_as_float((uint32_t)(ni - h + 127) << 23);
+    return (p * s1) * s2;
+}
+// pow(x, y) = exp(y * log(x)) for x >= 0 (polynomial mutation); pow(0, y > 0) = 0; x < 0 -> NaN
+QDX_DEV float qdx_powf(float x, float y) {
+    if (x != x || y != y) return __int_as_float(0x7fc00000);
+    if (x < 0.0f) return __int_as_float(0x7fc00000);
+    if (x == 0.0f) return y > 0.0f ? 0.0f : (y == 0.0f ? 1.0f : INFINITY);
+    if (x == INFINITY) return y > 0.0f ? INFINITY : (y == 0.0f ? 1.0f : 0.0f);
+    float lg;
+    if (x < 0x1p-126f) lg = qdx_logf(x * 0x1p+25f) - 0x1.154246p+4f;
+    else lg = qdx_logf(x);
+    return qdx_expf(y * lg);
+}
+
 // Total order key for a fitness: -inf < ... < -0 == +0 < ... < +inf < NaN (NaN = 0xFFFFFFFF).
 QDX_DEV uint32_t qdx_order_key(float v) {
     if (v != v) return 0xFFFFFFFFu;

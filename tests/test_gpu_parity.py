@@ -91,6 +91,57 @@ def test_isoline_variation_dense(dev, co, B, D):
         assert np.allclose(got, ref, rtol=RTOL, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,D,prop,eta", [(64, 100, 0.1, 10.0), (33, 20, 0.5, 20.0), (5, 2000, 0.05, 5.0), (300, 7, 1.0, 1.0), (17, 64, 0.0, 3.0)])
+def test_polynomial_mutation(dev, co, B, D, prop, eta):
+    """reference mutation_operators.py:12-117; D = 2000 exercises the two-round permutation."""
+    from qdax_b200.core.emitters.mutation_operators import polynomial_mutation
+
+    rng = np.random.default_rng(B + D)
+    x = rng.random((B, D)).astype(np.float32)
+    x[0, : min(D, 4)] = [0.0, 1.0, 0.5, 1e-30][: min(D, 4)]
+    got = N(polynomial_mutation(T(x, dev), jr.key(9), prop, eta, 0.0, 1.0))
+    ref = co.polynomial_mutation(x, jr.key(9), prop, eta, 0.0, 1.0)
+    assert np.array_equal(got, ref)
+    assert ((got != x).sum(axis=1) <= int(prop * D)).all() and got.min() >= 0.0 and got.max() <= 1.0
+    if D <= 100:   # literal NumPy restatement (np.power): same genes mutated, values within tolerance
+        lit = qn.polynomial_mutation(x, jr.key(9), prop, eta, 0.0, 1.0)
+        assert np.array_equal(got != x, lit != x) and np.allclose(got, lit, rtol=RTOL, atol=2e-6)
+
+
+@pytest.mark.parametrize("B,D,prop", [(64, 100, 0.3), (7, 12, 1.0), (1000, 33, 0.1)])
+def test_polynomial_crossover(dev, co, B, D, prop):
+    from qdax_b200.core.emitters.mutation_operators import polynomial_crossover
+
+    rng = np.random.default_rng(B * D)
+    x1, x2 = rng.random((B, D)).astype(np.float32), rng.random((B, D)).astype(np.float32)
+    got = N(polynomial_crossover(T(x1, dev), T(x2, dev), jr.key(4), prop))
+    assert np.array_equal(got, co.polynomial_crossover(x1, x2, jr.key(4), prop))
+    assert np.array_equal(got, qn.polynomial_crossover(x1, x2, jr.key(4), prop))
+
+
+def test_mixing_emitter_mixed_percentage(dev, co):
+    """variation_percentage < 1: crossover on the first int(B * pct) rows, mutation on the rest, and the reference's
+    key handling (standard_emitters.py:55,65: the SAME key is re-split for the mutation branch)."""
+    from qdax_b200.core.emitters.mutation_operators import polynomial_crossover, polynomial_mutation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+
+    K, D, B = 256, 20, 100
+    cent = qn.compute_euclidean_centroids((16, 16), 0.0, 1.0)
+    rep, g, fit, _ = _make_rep(dev, K, D, 0.5, 77, cent)
+    em = MixingEmitter(functools.partial(polynomial_mutation, proportion_to_mutate=0.2, eta=10.0, minval=0.0, maxval=1.0),
+                       functools.partial(polynomial_crossover, proportion_var_to_change=0.5), 0.6, B)
+    key = jr.key(21)
+    x, _ = em.emit(rep, None, key)
+    nv, nm = int(B * 0.6), B - int(B * 0.6)
+    k3 = jr.split(key, 3)
+    x1 = g[co.select_indices(fit, k3[0], nv)]
+    x2 = g[co.select_indices(fit, k3[1], nv)]
+    xv = co.polynomial_crossover(x1, x2, k3[2], 0.5)
+    k2 = jr.split(key)
+    xm = co.polynomial_mutation(g[co.select_indices(fit, k2[0], nm)], k2[1], 0.2, 10.0, 0.0, 1.0)
+    assert np.array_equal(N(x), np.concatenate([xv, xm], axis=0))
+
+
 def _make_rep(dev, K, D, occ, seed, centroids):
     from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
 
