@@ -62,8 +62,10 @@ int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t*
  * isoline_variation (mutation_operators.py:205,220).
  * key_mode: 0 keep keys | 1 (k0,k1) = key of MAPElites.update | 2 advance the workspace carry key
  * (scan_update) | 3 (k0,k1) = key of DistributedMAPElites.update | 4 (k0,k1) = key of MixingEmitter.emit */
+/* rank_slot >= 0 additionally publishes this rank's generation keys in tail slot `rank_slot` of the key table so that
+ * they travel with the all-reduce of the multi-GPU exchange (-1: single GPU). */
 int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t key_mode, uint32_t k0, uint32_t k1,
-                       void* stream);
+                       int32_t rank_slot, void* stream);
 
 /* ---- stages (a)+(b)[+(c grid)+(d offer)] fused.  Replaces MixingEmitter.emit with variation_percentage=1
  * (standard_emitters.py:51-62: two UniformSelector.select + isoline_variation), the task scoring function,
@@ -100,7 +102,8 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
                  uint32_t idx_base, int32_t first_wins, void* stream);
 
 /* ---- stage (d): MapElitesRepertoire.add (mapelites_repertoire.py:173-266).
- * qdx_offer_cells: segment_max + tie-break as a packed (fitness-key, index) 64-bit atomicMax per cell.
+ * qdx_offer_cells: segment_max + tie-break as a packed (32-bit fitness key, 31-bit index) atomicMax per cell
+ * (offspring indices idx_base + i must stay below 2^31).
  * qdx_commit: scatter of the winners' genotype / fitness / descriptor rows into the repertoire (in place),
  * key-table reset, and default_qd_metrics (qdax/utils/metrics.py:74-98) -> metrics_out4 (device, optional).
  * mode 0: offspring rows indexed by (winner index - idx_base).  Modes 1 / 2 split the commit around an exchange
@@ -113,6 +116,14 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
                const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
                float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
                int32_t mode, void* stream);
+
+/* Multi-GPU "regen" exchange (DistributedMAPElites.update, distributed_map_elites.py:133-146, without moving genotypes):
+ * after an all-reduce(max) over the key table (K keys + 8 * 64 key slots, int64, all values < 2^63) every rank
+ * recomputes the elected winners from (owner's generation keys, local index) into per-cell staging rows; score the
+ * staging rows with qdx_score and apply them with qdx_commit(mode 2).  Global index = rank * B_dev + i. */
+int qdx_regenerate_winners(void* ws, int64_t K, int64_t D, int64_t B_dev, int32_t nranks, const float* rep_genotypes,
+                           float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
+                           int32_t first_wins, float* stage_genotypes, void* stream);
 
 /* ---- pieces of the preserved Python surface ---- */
 /* UniformSelector.select index stream for the key handed to select() (uniform_selector.py:48-55) */

@@ -50,7 +50,8 @@ PROTOTYPES = {
     "qdx_workspace_init": [_vp, _i64, _vp],
     "qdx_workspace_set_carry_key": [_vp, _u32, _u32, _vp],
     "qdx_workspace_read": [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_i32), _vp],
-    "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _vp],
+    "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
+    "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],
     "qdx_generate": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _i32,
                      C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],
@@ -94,7 +95,7 @@ def lib() -> C.CDLL:
 
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
-KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
+KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
                    "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0

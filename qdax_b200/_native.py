@@ -57,11 +57,13 @@ class Workspace:
     def ptr(self) -> C.c_void_p:
         return _ptr(self.buf)
 
-    def keytab(self) -> torch.Tensor:
-        """int64 view of the K packed 64-bit insertion keys (what the winners-only multi-GPU exchange reduces)."""
+    def keytab(self, with_key_slots: bool = False) -> torch.Tensor:
+        """int64 view of the K packed insertion keys (all < 2^63, so signed max == unsigned max); with_key_slots also
+        covers the 8 * 64 tail slots that carry every rank's generation keys through the same all-reduce."""
         off = C.c_int64(0)
         call("qdx_workspace_keytab_offset", C.c_int64(self.K), C.byref(off))
-        return self.buf[off.value: off.value + self.K * 8].view(torch.int64)
+        n = self.K + (8 * 64 if with_key_slots else 0)
+        return self.buf[off.value: off.value + n * 8].view(torch.int64)
 
     def set_carry_key(self, key) -> None:
         k0, k1 = key_words(key)
@@ -160,10 +162,18 @@ def _grid_ptr(grid: Optional[Grid]):
 
 
 # ------------------------------------------------------------------------------------------ kernels
-def select_prepare(rep_f: torch.Tensor, ws: Workspace, key_mode: int = KEYMODE_KEEP, key=None) -> None:
+def select_prepare(rep_f: torch.Tensor, ws: Workspace, key_mode: int = KEYMODE_KEEP, key=None, rank_slot: int = -1) -> None:
     k0, k1 = key_words(key) if key is not None else (0, 0)
     call("qdx_select_prepare", _ptr(rep_f), C.c_int64(rep_f.numel()), ws.ptr, C.c_int32(key_mode), C.c_uint32(k0),
-         C.c_uint32(k1), _stream())
+         C.c_uint32(k1), C.c_int32(rank_slot), _stream())
+
+
+def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: int, iso_sigma: float, line_sigma: float, minval,
+                       maxval, first_wins: bool, stage_g: torch.Tensor) -> None:
+    K, D = rep_g.shape
+    call("qdx_regenerate_winners", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B_dev), C.c_int32(nranks), _ptr(rep_g),
+         C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
+         C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(bool(first_wins)), _ptr(stage_g), _stream())
 
 
 def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, line_sigma: float, minval, maxval,
@@ -177,11 +187,12 @@ def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, l
          _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), _stream())
 
 
-def score(task: str, g: torch.Tensor, desc_dim: int = 2) -> Tuple[torch.Tensor, torch.Tensor]:
+def score(task: str, g: torch.Tensor, desc_dim: int = 2, out_f: Optional[torch.Tensor] = None,
+          out_d: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     g = require_cuda(g, "genotypes")
     B, D = g.shape
-    f = torch.empty(B, dtype=torch.float32, device=g.device)
-    d = torch.empty(B, desc_dim, dtype=torch.float32, device=g.device)
+    f = torch.empty(B, dtype=torch.float32, device=g.device) if out_f is None else out_f
+    d = torch.empty(B, desc_dim, dtype=torch.float32, device=g.device) if out_d is None else out_d
     call("qdx_score", C.c_int32(TASK_IDS[task]), _ptr(g), C.c_int64(B), C.c_int64(D), C.c_int32(desc_dim), _ptr(f), _ptr(d), _stream())
     return f, d
 

@@ -7,6 +7,11 @@ rank * B_dev + i), same per-rank key chain (`key, subkey = split(key)`; emit(sub
 
   exchange="allgather"  reference-faithful: the offspring tuples (+ their cells, computed on the shard) are
                         all-gathered, every rank offers the full batch and commits from the gathered rows.
+  exchange="regen"      nothing but 64-bit keys travels: each rank offers its shard into its local key table (global
+                        indices), ONE all-reduce(max) of the K keys elects the per-cell winners and carries every
+                        rank's generation keys in tail slots; every rank then REGENERATES the winners from (owner's
+                        keys, local index) -- the RNG is counter-based and the repertoire replicated -- scores them
+                        and commits.  No genotype crosses NVLink.
   exchange="winners"    only what can change the repertoire travels: each rank offers its shard into its local
                         64-bit key table, one all-reduce(max) of the K keys elects the global per-cell winners
                         (the global best of a cell is always a local best), winners' rows are merged through a
@@ -32,8 +37,8 @@ from qdax_b200.core.map_elites import MAPElites
 class DistributedMAPElites(MAPElites):
     def __init__(self, *args, exchange: str = "allgather", group=None, **kwargs) -> None:
         super().__init__(*args, **kwargs)
-        if exchange not in ("allgather", "winners"):
-            raise ValueError("exchange must be 'allgather' or 'winners'")
+        if exchange not in ("allgather", "winners", "regen"):
+            raise ValueError("exchange must be 'allgather', 'winners' or 'regen'")
         self._exchange = exchange
         self._group = group
         self._dist_buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
@@ -78,10 +83,10 @@ class DistributedMAPElites(MAPElites):
         rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
         first = rep.tie_break == "first"
-        winners = self._exchange == "winners"
+        winners = self._exchange in ("winners", "regen")
         base = rank * B
         self._mark("begin")
-        _native.select_prepare(rep_f, ws, key_mode, key)
+        _native.select_prepare(rep_f, ws, key_mode, key, rank_slot=rank if self._exchange == "regen" else -1)
         self._mark("prepare")
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], Dd, grid, winners and grid is not None, base, first,
@@ -105,11 +110,20 @@ class DistributedMAPElites(MAPElites):
                            qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
             self._mark("commit")
             return
-        keytab = ws.keytab()
-        parallel.all_reduce_max_u64_(keytab, self._group)
         st = gb["stage"]
-        st.zero_()
         sg, sd, sf = _stage_views(st, D, Dd)
+        if self._exchange == "regen":
+            parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
+            _native.regenerate_winners(ws, rep.genotypes, B, R, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"], cfg["maxval"],
+                                       first, sg)
+            _native.score(cfg["task"], sg, Dd, out_f=sf, out_d=sd)
+            self._mark("exchange")
+            _native.commit(ws, sg, sf, sd, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
+                           metrics_out=metrics_out, mode=2)
+            self._mark("commit")
+            return
+        parallel.all_reduce_max_i64_(ws.keytab(), self._group)
+        st.zero_()
         _native.commit(ws, buf["g"], buf["f"], buf["d"], sg, sf, sd, idx_base=base, first_wins=first, mode=1)
         parallel.all_reduce_disjoint_rows_(st, self._group)
         self._mark("exchange")

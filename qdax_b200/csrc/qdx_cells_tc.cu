@@ -453,7 +453,7 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
                  uint32_t idx_base, int32_t first_wins, void* stream) {
     if (!desc || !centroids || !prep || !scratch || !out_cells || B < 0 || K <= 0 || desc_dim < 1 || desc_dim > tc::KD) return QDX_ERR_ARG;
     if (offer && (!ws || !rep_fitness || !fitness)) return QDX_ERR_ARG;
-    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     QdxTcParams p;

@@ -38,8 +38,9 @@ __host__ __device__ inline size_t qdx_ws_occ_offset() { return qdx_align_up(size
 __host__ __device__ inline size_t qdx_ws_keytab_offset(int64_t K) {
     return qdx_align_up(qdx_ws_occ_offset() + sizeof(int32_t) * (size_t)K, 256);
 }
+#define QDX_MAX_RANKS 64      // generation keys of up to 64 ranks ride in the tail of the key table (8 slots each)
 __host__ __device__ inline size_t qdx_ws_total_bytes(int64_t K) {
-    return qdx_align_up(qdx_ws_keytab_offset(K) + sizeof(unsigned long long) * (size_t)K, 256);
+    return qdx_align_up(qdx_ws_keytab_offset(K) + sizeof(unsigned long long) * (size_t)(K + 8 * QDX_MAX_RANKS), 256);
 }
 __host__ __device__ inline int32_t* qdx_ws_occ(void* ws) { return (int32_t*)((char*)ws + qdx_ws_occ_offset()); }
 __host__ __device__ inline unsigned long long* qdx_ws_keytab(void* ws, int64_t K) {
@@ -58,9 +59,15 @@ struct QdxGrid {
     int32_t total_axes;
 };
 
-// Packed 64-bit insertion key: (order_key(fitness) << 32) | (first_wins ? ~idx : idx); 0 = empty slot.
+// Packed insertion key, 63 bits: (order_key(fitness) << 31) | (first_wins ? ~idx : idx) & 0x7FFFFFFF; 0 = empty slot.
+// Bit 63 is never set, so unsigned order == signed order and the multi-GPU all-reduce(max) can run on int64.
 QDX_DEV unsigned long long qdx_pack_key(float f, uint32_t idx, int first_wins) {
-    return ((unsigned long long)qdx_order_key(f) << 32) | (unsigned long long)(first_wins ? ~idx : idx);
+    return ((unsigned long long)qdx_order_key(f) << 31) | (unsigned long long)((first_wins ? ~idx : idx) & 0x7FFFFFFFu);
+}
+QDX_DEV bool qdx_key_is_nan(unsigned long long key) { return (uint32_t)(key >> 31) == 0xFFFFFFFFu; }
+QDX_DEV uint32_t qdx_key_index(unsigned long long key, int first_wins) {
+    const uint32_t lo = (uint32_t)key & 0x7FFFFFFFu;
+    return first_wins ? (~lo & 0x7FFFFFFFu) : lo;
 }
 
 // Offer offspring `idx` with fitness f to cell c (MapElitesRepertoire.add, mapelites_repertoire.py:211-231):

@@ -36,19 +36,29 @@ __device__ void qdx_derive_gen_keys(QdxKey emit, QdxGenKeys* out) {
 // key_mode: 0 keep keys; 1 `key` = key of MAPElites.update; 2 scan step on ws->carry; 3 `key` = key of
 // DistributedMAPElites.update; 4 `key` = emit key.
 __global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restrict__ rep_f, int64_t K, void* ws_raw,
-                                                           QdxKey key, int key_mode) {
+                                                           QdxKey key, int key_mode, int rank_slot) {
     QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
     int32_t* occ = qdx_ws_occ(ws_raw);
     __shared__ int32_t s_warp[32];
     __shared__ int32_t s_total;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
 
+    if (rank_slot >= 0) {     // the other ranks' key slots must be empty before the all-reduce(max) fills them
+        unsigned long long* slots = qdx_ws_keytab(ws_raw, K) + K;
+        for (int j = t; j < 8 * QDX_MAX_RANKS; j += blockDim.x) if ((j >> 3) != rank_slot) slots[j] = 0ull;
+    }
     if (t == 32 && key_mode != 0) {      // key chain on warp 1, overlapping the scan
         if (key_mode == 2) { QdxKey c = ws->carry; key = qdx_split(c, 1); ws->carry = qdx_split(c, 0); }  // map_elites.py:214
         QdxKey emit = key;
         if (key_mode == 1 || key_mode == 2) emit = qdx_split(qdx_split(key, 1), 1);                         // :177, :241
         else if (key_mode == 3) emit = qdx_split(key, 1);                                // distributed_map_elites.py:124
         qdx_derive_gen_keys(emit, &ws->keys);
+        if (rank_slot >= 0) {   // publish this rank's generation keys behind the key table: they ride in the same all-reduce
+            unsigned long long* slot = qdx_ws_keytab(ws_raw, K) + K + 8 * rank_slot;
+            const QdxGenKeys g = ws->keys;
+            const uint32_t w[8] = {g.sel1.a, g.sel1.b, g.sel2.a, g.sel2.b, g.line.a, g.line.b, g.leaf.a, g.leaf.b};
+            for (int j = 0; j < 8; ++j) slot[j] = (unsigned long long)w[j];
+        }
     }
 
     const int64_t chunk = (K + blockDim.x - 1) / blockDim.x;
@@ -548,15 +558,14 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
         const int64_t c = c0 + lane;
         unsigned long long key = c < K ? keytab[c] : 0ull;
         if (c < K && key != 0ull && mode != 1) keytab[c] = 0ull;
-        const bool win = key != 0ull && (uint32_t)(key >> 32) != 0xFFFFFFFFu;      // NaN-poisoned cells accept nobody
+        const bool win = key != 0ull && !qdx_key_is_nan(key);                      // NaN-poisoned cells accept nobody
         unsigned m = __ballot_sync(0xffffffffu, win);
         added += __popc(m);
         while (m) {
             const int src = __ffs(m) - 1; m &= m - 1;
             const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
-            const uint32_t lo = (uint32_t)k;
             const int64_t cell = c0 + src;
-            int64_t i = (int64_t)(first_wins ? ~lo : lo) - (int64_t)idx_base;
+            int64_t i = (int64_t)qdx_key_index(k, first_wins) - (int64_t)idx_base;
             if (mode == 2) i = cell;
             else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) ws->error = QDX_ERR_BAD_INDEX; continue; }
             const float* srow = off_g + i * D; float* drow = rep_g + cell * D;
@@ -610,6 +619,55 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
         out[3] = (float)(int)(*(volatile uint32_t*)&ws->pad[0]);                           // offspring inserted by this call
         for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (metrics_out) metrics_out[j] = out[j]; }
         ws->ticket = 0u; ws->pad[0] = 0u;
+    }
+}
+
+// =====================================================================================================
+// regenerate the elected winners (multi-GPU "regen" exchange)
+// =====================================================================================================
+// After the all-reduce(max) of the key table every rank knows, per cell, the global index of the winning offspring
+// and (tail slots) every rank's generation keys.  The RNG is counter-based and the repertoire is replicated, so the
+// winner's genotype is recomputed locally, bit for bit as its owner produced it, into a per-cell staging row -- no
+// genotype crosses NVLink.  One warp per elected cell.
+__global__ void __launch_bounds__(256) qdx_regen_kernel(void* ws_raw, int64_t K, int32_t D, int64_t B_dev, int32_t nranks,
+                                                        const float* __restrict__ rep_g, float iso_sigma, float line_sigma,
+                                                        int32_t has_min, float minv, int32_t has_max, float maxv,
+                                                        int32_t first_wins, float* __restrict__ stage_g) {
+    __shared__ QdxSeg s_seg[QDX_MAX_SEG];
+    __shared__ float s_last[QDX_MAX_SEG];
+    const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
+    const int nseg = ws->sel.nseg;
+    for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
+    __syncthreads();
+    if (nseg <= 0) return;
+    const unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
+    const int32_t* __restrict__ occ = qdx_ws_occ(ws_raw);
+    const float total = ws->sel.total;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp_global; c < K; c += nwarps) {
+        const unsigned long long key = keytab[c];
+        if (key == 0ull || qdx_key_is_nan(key)) continue;
+        const uint32_t idx = qdx_key_index(key, first_wins);
+        const int64_t r = idx / B_dev, i = idx % B_dev;
+        if (r >= nranks) continue;
+        const unsigned long long* slot = keytab + K + 8 * r;
+        const QdxKey sel1{(uint32_t)slot[0], (uint32_t)slot[1]}, sel2{(uint32_t)slot[2], (uint32_t)slot[3]};
+        const QdxKey kline{(uint32_t)slot[4], (uint32_t)slot[5]}, kleaf{(uint32_t)slot[6], (uint32_t)slot[7]};
+        const float u1 = qdx_unit_float(qdx_bits32(sel1, (uint64_t)i)), u2 = qdx_unit_float(qdx_bits32(sel2, (uint64_t)i));
+        const int32_t p1 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u1)) - 1];
+        const int32_t p2 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u2)) - 1];
+        const float ln = qdx_normal_from_bits(qdx_bits32(kline, (uint64_t)i)) * line_sigma;
+        for (int d = lane; d < D; d += 32) {
+            const float a = __ldg(rep_g + (int64_t)p1 * D + d), b = __ldg(rep_g + (int64_t)p2 * D + d);
+            const float iso = qdx_normal_from_bits(qdx_bits32(kleaf, (uint64_t)i * (uint64_t)D + (uint64_t)d)) * iso_sigma;
+            float t1 = a + iso, t2 = b - a, t3 = t2 * ln;
+            float x = t1 + t3;
+            if (has_min) x = qdx_max_nanprop(x, minv);
+            if (has_max) x = qdx_min_nanprop(x, maxv);
+            stage_g[c * D + d] = x;
+        }
     }
 }
 
@@ -786,9 +844,10 @@ int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t*
     return 0;
 }
 
-int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t key_mode, uint32_t k0, uint32_t k1, void* stream) {
-    if (!rep_fitness || !ws || K <= 0 || key_mode < 0 || key_mode > 4) return QDX_ERR_ARG;
-    qdx_prepare_kernel<<<1, 1024, 0, S(stream)>>>(rep_fitness, K, ws, QdxKey{k0, k1}, key_mode);
+int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t key_mode, uint32_t k0, uint32_t k1,
+                       int32_t rank_slot, void* stream) {
+    if (!rep_fitness || !ws || K <= 0 || key_mode < 0 || key_mode > 4 || rank_slot >= QDX_MAX_RANKS) return QDX_ERR_ARG;
+    qdx_prepare_kernel<<<1, 1024, 0, S(stream)>>>(rep_fitness, K, ws, QdxKey{k0, k1}, key_mode, rank_slot);
     QDX_CHECK_LAUNCH();
     return 0;
 }
@@ -803,7 +862,7 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
     if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
     if (task == QDX_TASK_ARM && desc_dim != 2) return QDX_ERR_ARG;
     if (task == QDX_TASK_NONE && (!out_genotypes || offer)) return QDX_ERR_ARG;
-    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
     if (B == 0) return 0;
     QdxGenParams p;
     memset(&p, 0, sizeof(p));
@@ -852,7 +911,7 @@ int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centr
               uint32_t idx_base, int32_t first_wins, void* stream) {
     if (!desc || !centroids || !out_cells || B < 0 || K <= 0 || desc_dim < 1) return QDX_ERR_ARG;
     if (offer && (!ws || !rep_fitness || !fitness)) return QDX_ERR_ARG;
-    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
     if (B == 0) return 0;
     QdxGrid g;
     int rc = fill_grid(grid, desc_dim, &g);
@@ -886,7 +945,7 @@ int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centr
 int qdx_offer_cells(const int32_t* cells, const float* fitness, int64_t B, int64_t K, void* ws, const float* rep_fitness,
                     uint32_t idx_base, int32_t first_wins, void* stream) {
     if (!cells || !fitness || !ws || !rep_fitness || B < 0 || K <= 0) return QDX_ERR_ARG;
-    if ((uint64_t)idx_base + (uint64_t)B > 0xFFFFFFFFull) return QDX_ERR_ARG;
+    if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
     if (B == 0) return 0;
     qdx_offer_kernel<<<(unsigned)((B + 255) / 256), 256, 0, S(stream)>>>(cells, fitness, B, K, ws, rep_fitness, idx_base, first_wins);
     QDX_CHECK_LAUNCH();
@@ -906,6 +965,18 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
     qdx_commit_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
                                                             idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
                                                             qd_offset, metrics_out4, added_cells, mode);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_regenerate_winners(void* ws, int64_t K, int64_t D, int64_t B_dev, int32_t nranks, const float* rep_genotypes,
+                           float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
+                           int32_t first_wins, float* stage_genotypes, void* stream) {
+    if (!ws || !rep_genotypes || !stage_genotypes || K <= 0 || D <= 0 || B_dev <= 0 || nranks < 1 || nranks > QDX_MAX_RANKS) return QDX_ERR_ARG;
+    int64_t ctas = (K + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    qdx_regen_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, B_dev, nranks, rep_genotypes, iso_sigma, line_sigma,
+                                                           has_min, minval, has_max, maxval, first_wins, stage_genotypes);
     QDX_CHECK_LAUNCH();
     return 0;
 }

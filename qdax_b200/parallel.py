@@ -47,6 +47,15 @@ def all_reduce_max_u64_(keys_i64: torch.Tensor, group=None) -> torch.Tensor:
     return keys_i64
 
 
+def all_reduce_max_i64_(keys_i64: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place element-wise max across ranks of the packed insertion keys (63-bit, never negative) and of the
+    generation-key slots that ride behind them."""
+    _, size = world(group)
+    if size > 1:
+        dist.all_reduce(keys_i64, op=dist.ReduceOp.MAX, group=group)
+    return keys_i64
+
+
 def all_reduce_disjoint_rows_(staging: torch.Tensor, group=None) -> torch.Tensor:
     """In-place merge of per-cell staging rows of which at most ONE rank holds a non-zero copy: an integer SUM over
     the raw 32-bit patterns is then an exact bitwise merge (a float sum would lose the sign of -0.0)."""

@@ -146,15 +146,16 @@ def okey(v):
 tab = np.zeros(K, np.uint64)
 for i in range(rank * B, (rank + 1) * B):
     if Fall[i] > rep_f[cells[i]]:
-        tab[cells[i]] = max(tab[cells[i]], (okey(Fall[i:i+1])[0] << np.uint64(32)) | np.uint64((~np.uint32(i)) & 0xFFFFFFFF))
+        tab[cells[i]] = max(tab[cells[i]], (okey(Fall[i:i+1])[0] << np.uint64(31)) | np.uint64((~np.uint32(i)) & 0x7FFFFFFF))
+assert (tab < np.uint64(1) << np.uint64(63)).all()          # 63-bit keys: signed max == unsigned max
 t = torch.from_numpy(tab.view(np.int64).copy())
-parallel.all_reduce_max_u64_(t)
+parallel.all_reduce_max_i64_(t)
 win = t.numpy().view(np.uint64)
 _, f2, _, sidx = co.add(np.zeros((K, D)), rep_f, np.zeros((K, 2)), Gall, Fall, Dall, cells, "first")
 exp = np.full(K, -1)
 for i in range(world * B - 1, -1, -1):
     if sidx[i] < K: exp[sidx[i]] = i
-got = np.where(win != 0, (~(win & 0xFFFFFFFF).astype(np.uint32)).astype(np.int64), -1)
+got = np.where(win != 0, ((~(win & np.uint64(0x7FFFFFFF)).astype(np.uint32)) & np.uint32(0x7FFFFFFF)).astype(np.int64), -1)
 assert np.array_equal(got, exp)
 dist.barrier()
 if rank == 0: print("GLOO_OK")
