@@ -22,6 +22,8 @@ struct QdxGenKeys {
     QdxKey leaf;    // split(split(split(emit,3)[2])[0], 1)[0] -> iso noise
 };
 
+#define QDX_MAX_COMMIT_CTAS (148 * 8)
+
 // Device workspace header (one per repertoire); arrays follow at fixed offsets (qdx_ws_* below).
 struct QdxWorkspace {
     QdxSel sel;             // selection segments of the current repertoire
@@ -31,6 +33,12 @@ struct QdxWorkspace {
     uint32_t ticket;        // last-CTA-done counter of the commit kernel
     int32_t error;          // sticky device-side error flag (e.g. empty repertoire)
     uint32_t pad[2];
+    // per-CTA partial metrics of the commit kernel, summed in CTA order by the last CTA (deterministic)
+    double part_sum[QDX_MAX_COMMIT_CTAS];
+    float part_max[QDX_MAX_COMMIT_CTAS];
+    int32_t part_cnt[QDX_MAX_COMMIT_CTAS];
+    int32_t part_add[QDX_MAX_COMMIT_CTAS];
+    int32_t part_nan[QDX_MAX_COMMIT_CTAS];
 };
 
 __host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

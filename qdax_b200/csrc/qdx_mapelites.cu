@@ -553,72 +553,90 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int added = 0;
-    for (int64_t c0 = warp_global * 32; c0 < K; c0 += nwarps * 32) {
-        // one coalesced 64-bit load per lane covers 32 cells; then the warp copies each changed row
-        const int64_t c = c0 + lane;
-        unsigned long long key = c < K ? keytab[c] : 0ull;
-        if (c < K && key != 0ull && mode != 1) keytab[c] = 0ull;
-        const bool win = key != 0ull && !qdx_key_is_nan(key);                      // NaN-poisoned cells accept nobody
-        unsigned m = __ballot_sync(0xffffffffu, win);
-        added += __popc(m);
-        while (m) {
-            const int src = __ffs(m) - 1; m &= m - 1;
-            const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
-            const int64_t cell = c0 + src;
-            int64_t i = (int64_t)qdx_key_index(k, first_wins) - (int64_t)idx_base;
+    double sum = 0.0; float mx = -INFINITY; int cnt = 0; int nan = 0;      // metrics of this warp's cells (lane 0)
+    // One warp per CELL (grid-stride): every resident warp has a winner row in flight, which is what lets the row
+    // traffic approach the HBM roofline when rows are large (K/32-warp parallelism measured 35 % of peak).
+    unsigned long long key_next = (lane == 0 && warp_global < K) ? keytab[warp_global] : 0ull;     // lane 0 owns the table entries
+    for (int64_t cell = warp_global; cell < K; cell += nwarps) {
+        const unsigned long long key = __shfl_sync(0xffffffffu, key_next, 0);
+        if (lane == 0 && cell + nwarps < K) key_next = keytab[cell + nwarps];                        // prefetch the next entry
+        float fcell;
+        const bool win = key != 0ull && !qdx_key_is_nan(key);                // NaN-poisoned cells accept nobody
+        int64_t i = -1;
+        if (win) {
+            i = (int64_t)qdx_key_index(key, first_wins) - (int64_t)idx_base;
             if (mode == 2) i = cell;
-            else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) ws->error = QDX_ERR_BAD_INDEX; continue; }
+            else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) ws->error = QDX_ERR_BAD_INDEX; i = -1; }
+        }
+        if (i >= 0) {
             const float* srow = off_g + i * D; float* drow = rep_g + cell * D;
             if ((D & 3) == 0) {
                 const float4* s4 = reinterpret_cast<const float4*>(srow); float4* d4 = reinterpret_cast<float4*>(drow);
-                for (int q = lane; q < (D >> 2); q += 32) d4[q] = __ldg(s4 + q);
+                const int nq = D >> 2;
+                int q = lane;
+                for (; q + 96 < nq; q += 128) {
+                    const float4 v0 = __ldcs(s4 + q), v1 = __ldcs(s4 + q + 32), v2 = __ldcs(s4 + q + 64), v3 = __ldcs(s4 + q + 96);
+                    d4[q] = v0; d4[q + 32] = v1; d4[q + 64] = v2; d4[q + 96] = v3;
+                }
+                for (; q < nq; q += 32) d4[q] = __ldg(s4 + q);
             } else {
                 for (int d = lane; d < D; d += 32) drow[d] = srow[d];
             }
             for (int d = lane; d < Dd; d += 32) rep_d[cell * Dd + d] = off_d[i * Dd + d];
-            if (lane == 0) { rep_f[cell] = off_f[i]; if (added_cells) added_cells[cell] = (int32_t)i; }
+            fcell = off_f[i];
+            if (lane == 0) { rep_f[cell] = fcell; if (added_cells) added_cells[cell] = (int32_t)i; }
+            ++added;
+        } else {
+            fcell = (mode == 1) ? -INFINITY : __ldcg(rep_f + cell);
         }
+        if (key != 0ull && mode != 1 && lane == 0) keytab[cell] = 0ull;
+        if (fcell != -INFINITY) { sum += (double)fcell; ++cnt; }
+        if (fcell != fcell) nan = 1; else if (fcell > mx) mx = fcell;
     }
-    // ---- metrics by the last CTA to finish (deterministic fixed-shape reduction) -------------------------
+    // ---- metrics: CTAs publish partials of their cells, the last CTA to finish sums them in CTA order (deterministic)
+    if (mode == 1) return;
     __shared__ double s_sum[8]; __shared__ float s_max[8]; __shared__ int s_cnt[8]; __shared__ int s_nan[8]; __shared__ int s_add[8];
     __shared__ bool s_last;
-    if (mode == 1) return;
-    if (lane == 0) s_add[threadIdx.x >> 5] = added;
-    __threadfence();
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int a = 0; for (int w = 0; w < (blockDim.x >> 5); ++w) a += s_add[w];
-        atomicAdd((int*)&ws->pad[0], a);
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; }
+        ws->part_sum[blockIdx.x] = s; ws->part_max[blockIdx.x] = m; ws->part_cnt[blockIdx.x] = n; ws->part_nan[blockIdx.x] = nn;
+        ws->part_add[blockIdx.x] = a;
+        __threadfence();
         const unsigned t = atomicAdd(&ws->ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    double sum = 0.0; float mx = -INFINITY; int cnt = 0; int nan = 0;
-    for (int64_t c = threadIdx.x; c < K; c += blockDim.x) {
-        const float v = __ldcg(rep_f + c);
-        if (v != -INFINITY) { sum += (double)v; ++cnt; }
-        if (v != v) nan = 1; else if (v > mx) mx = v;
+    // fixed-shape reduction of the per-CTA partials: thread t sums partials t, t+256, ... then warps, then thread 0
+    {
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            s += *(volatile double*)&ws->part_sum[b]; m = fmaxf(m, *(volatile float*)&ws->part_max[b]);
+            n += *(volatile int32_t*)&ws->part_cnt[b]; nn |= *(volatile int32_t*)&ws->part_nan[b]; a += *(volatile int32_t*)&ws->part_add[b];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            n += __shfl_xor_sync(0xffffffffu, n, o); nn |= __shfl_xor_sync(0xffffffffu, nn, o); a += __shfl_xor_sync(0xffffffffu, a, o);
+        }
+        __syncthreads();
+        if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; }
+        __syncthreads();
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
-    }
-    if (lane == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; s_cnt[threadIdx.x >> 5] = cnt; s_nan[threadIdx.x >> 5] = nan; }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; }
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; }
         float out[4];
         out[0] = (float)s + qd_offset * (float)n;                 // qd_score   (metrics.py:92-93)
         out[1] = nn ? NAN : m;                                     // max_fitness (:95)
         out[2] = 100.0f * __fdiv_rn((float)n, (float)K);           // coverage   (:94)
-        out[3] = (float)(int)(*(volatile uint32_t*)&ws->pad[0]);                           // offspring inserted by this call
+        out[3] = (float)a;                                         // offspring inserted by this call
         for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (metrics_out) metrics_out[j] = out[j]; }
-        ws->ticket = 0u; ws->pad[0] = 0u;
+        ws->ticket = 0u;
     }
 }
 
@@ -958,9 +976,8 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
                int32_t mode, void* stream) {
     if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
     if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
-    int64_t warps = (K + 31) / 32;
-    int64_t ctas = (warps + 7) / 8;
-    if (ctas > 148 * 8) ctas = 148 * 8;
+    int64_t ctas = (K + 7) / 8;                 // one warp per cell, 8 warps per CTA, grid-stride beyond 148 * 8 CTAs
+    if (ctas > QDX_MAX_COMMIT_CTAS) ctas = QDX_MAX_COMMIT_CTAS;
     if (ctas < 1) ctas = 1;
     qdx_commit_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
                                                             idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
