@@ -335,8 +335,15 @@ def run_gpu(args, cfg):
     else:
         dom_bytes = (4 * Dd + 4) * B + K * Dd * 4
     dom_gbs = dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tr.get("%s@%s@n%d" % ({"generate": "qdx_generate_kernel", "cells": "qdx_cells_tc_kernel"}[dom], args.config, world))
+        traffic = ent["traffic_bytes"] if ent else None
+    except Exception:
+        pass
     roofline = {"kernel": {"generate": "qdx_generate_kernel", "cells": cells_kernel}[dom], "bound": "hbm", "achieved": dom_gbs,
-                "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kern_ms[dom],
                 "note": "ALU-bound kernel (one Threefry-2x32-20 block + erfinv per gene, sincos per joint): the HBM fraction is low by construction; see DESIGN.md section 6"}
     W = added_last
