@@ -244,13 +244,13 @@ def run_gpu(args, cfg):
             me._fused_distributed_generation(rep, fcfg, 3, sub, m)
             return key, m
         m = torch.empty(4, dtype=torch.float32, device=dev)
-        me._fused_generation(rep, fcfg, 2, None, m)
+        me._fused_generation(rep, fcfg, 2, None, m, carry)      # scan_update step: carry key advanced on the host
         return key, m
 
     fcfg = me._fused_config(rep)
     assert fcfg is not None, "bench configuration must take the fused native path"
     rep = rep._clone_state()
-    rep._workspace().set_carry_key(rank_key)
+    carry = np.array(rank_key, dtype=np.uint32)
     key = rank_key
     for _ in range(max(args.warmup, 3)):
         key, m = step(rep, key)
@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--exchange", default="regen", choices=["regen", "winners", "allgather"])
+    ap.add_argument("--exchange", default="regen", choices=["p2p", "regen", "winners", "allgather"])
     ap.add_argument("--cpu-sample", type=int, default=1 << 16, help="offspring per generation in the CPU arm")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

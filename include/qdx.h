@@ -25,6 +25,7 @@ extern "C" {
 #define QDX_ERR_EMPTY_REPERTOIRE (-3)  /* selection from an all-empty repertoire (p = 0/0 in the reference) */
 #define QDX_ERR_BAD_CELL (-4)          /* cell index out of range handed to qdx_offer_cells */
 #define QDX_ERR_BAD_INDEX (-5)         /* winner index outside the offspring buffer handed to qdx_commit */
+#define QDX_ERR_PEER_TIMEOUT (-6)      /* a peer's keys did not arrive within 2 s (peer-memory exchange) */
 
 /* task ids of the fused scoring functions */
 #define QDX_TASK_ID_NONE (-1)
@@ -73,12 +74,14 @@ int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t ke
  * (mapelites_repertoire.py:202-231).  task = QDX_TASK_ID_NONE: variation only (out_genotypes required).
  * Offspring i of this call has global index idx_base + i (rank * B_dev + i under DistributedMAPElites).
  * out_genotypes may be NULL when the offspring rows are not needed (winners are re-read by qdx_commit, so
- * pass NULL only with offer = 0). */
+ * pass NULL only with offer = 0).
+ * gen_keys8: the generation keys {sel1, sel2, line, leaf} derived on the host (qdx_host_generation_keys), or NULL
+ * to use the keys qdx_select_prepare left in the workspace. */
 int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
-                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, void* stream);
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, void* stream);
 
 /* ---- stage (b) standalone: arm_scoring_function / rastrigin_scoring_function / sphere_scoring_function */
 int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
@@ -125,6 +128,31 @@ int qdx_regenerate_winners(void* ws, int64_t K, int64_t D, int64_t B_dev, int32_
                            float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
                            int32_t first_wins, float* stage_genotypes, void* stream);
 
+/* Same, fused with the scoring of the regenerated rows (stage_fitness (K,), stage_desc (K, desc_dim) are written for
+ * the elected cells only), one warp per elected cell.  wait_peers != 0: first acquire-spin until every rank's keys of
+ * this generation have arrived in the local exchange buffer (peer-memory exchange below; bounded, QDX_ERR_PEER_TIMEOUT). */
+int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc_dim, int64_t B_dev, int32_t nranks,
+                      const float* rep_genotypes, float iso_sigma, float line_sigma, int32_t has_min, float minval,
+                      int32_t has_max, float maxval, int32_t first_wins, float* stage_genotypes, float* stage_fitness,
+                      float* stage_desc, int32_t wait_peers, void* stream);
+
+/* ---- peer-memory exchange: the all-gather + replicated add of DistributedMAPElites.update
+ * (distributed_map_elites.py:133-146) as direct NVLink traffic between the ranks' key tables, no collective library.
+ * Each rank owns an exchange buffer (arrival flags + two key tables, double-buffered by generation parity) created
+ * with cudaMalloc and exported with cudaIpc (64-byte handle, exchanged by the host: torch.distributed
+ * all_gather_object); qdx_xchg_attach records every rank's mapping in the workspace, after which offers go to the
+ * exchange table, qdx_xchg_push max-merges this rank's non-empty entries and its generation keys into every peer
+ * (system-scope atomicMax over NVLink) and raises its arrival flag there, and qdx_elect_winners(wait_peers = 1)
+ * consumes.  nranks <= 16.  All ranks must call the same sequence of generations (the epoch counter lives on the device).
+ * qdx_xchg_attach(nranks = 0) detaches. */
+int qdx_xchg_bytes(int64_t K, int64_t* bytes);
+int qdx_xchg_create(int64_t K, void** buf, void* ipc_handle64);
+int qdx_xchg_open(const void* ipc_handle64, void** peer_buf);
+int qdx_xchg_close(void* peer_buf);
+int qdx_xchg_destroy(void* buf);
+int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, void* stream);
+int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream);
+
 /* ---- pieces of the preserved Python surface ---- */
 /* UniformSelector.select index stream for the key handed to select() (uniform_selector.py:48-55) */
 int qdx_select_indices(void* ws, uint32_t k0, uint32_t k1, int64_t num, int32_t* out, void* stream);
@@ -155,6 +183,13 @@ int qdx_dns_add(const float* pop_genotypes, const float* pop_fitness, const floa
                 int32_t* survivors_scratch, void* stream);
 
 /* ---- host-only helpers (no GPU needed; used by the CPU test-suite) ---- */
+/* The jax.random.split chain from the key handed to MAPElites.update (key_mode 1; map_elites.py:177,241), one
+ * scan_update step on carry_io2 (2; :214, carry advanced in place), DistributedMAPElites.update (3;
+ * distributed_map_elites.py:124) or MixingEmitter.emit (4) down to the four stream keys of a generation
+ * {sel1, sel2, line, leaf} (standard_emitters.py:55, uniform_selector.py:48, mutation_operators.py:205,220). */
+/* jax.random.split(key, n) -> n keys of two words (partitionable Threefry: key i = threefry(key, counter (0, i))) */
+int qdx_host_split(uint32_t k0, uint32_t k1, int32_t n, uint32_t* out);
+int qdx_host_generation_keys(int32_t key_mode, uint32_t k0, uint32_t k1, uint32_t* carry_io2, uint32_t* out_keys8);
 int qdx_host_select_table(int32_t M, float* out_T, int32_t* out_nseg);
 int qdx_host_select_rank(int32_t M, const float* r, int64_t n, int32_t* out_rank);
 

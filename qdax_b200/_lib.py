@@ -19,6 +19,7 @@ ERRORS = {
     -3: "QDX_ERR_EMPTY_REPERTOIRE: selection from an all-empty repertoire",
     -4: "QDX_ERR_BAD_CELL: cell index out of range",
     -5: "QDX_ERR_BAD_INDEX: winner index outside the offspring buffer",
+    -6: "QDX_ERR_PEER_TIMEOUT: a peer's keys did not arrive (peer-memory exchange)",
 }
 
 
@@ -53,7 +54,18 @@ PROTOTYPES = {
     "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
     "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],
     "qdx_generate": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _i32,
-                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), _vp],
+    "qdx_elect_winners": [_vp, _i64, _i64, _i32, _i32, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
+                          _i32, _vp],
+    "qdx_xchg_bytes": [_i64, C.POINTER(_i64)],
+    "qdx_xchg_create": [_i64, C.POINTER(_vp), _vp],
+    "qdx_xchg_open": [_vp, C.POINTER(_vp)],
+    "qdx_xchg_close": [_vp],
+    "qdx_xchg_destroy": [_vp],
+    "qdx_xchg_attach": [_vp, _i32, _i32, C.POINTER(_vp), _vp],
+    "qdx_xchg_push": [_vp, _i64, C.POINTER(_u32), _vp],
+    "qdx_host_split": [_u32, _u32, _i32, _vp],
+    "qdx_host_generation_keys": [_i32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)],
     "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],
     "qdx_cells": [_vp, _i64, _i32, _vp, _i64, C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
     "qdx_cells_tc_workspace": [_i64, _i64, C.POINTER(_i64), C.POINTER(_i64)],
@@ -95,7 +107,7 @@ def lib() -> C.CDLL:
 
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
-KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
+KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
                    "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0

@@ -52,6 +52,11 @@ class Workspace:
         self.K = K
         self.buf = torch.empty(n.value, dtype=torch.uint8, device=device)
         call("qdx_workspace_init", _ptr(self.buf), C.c_int64(K), _stream())
+        # True once the occupied-cell list / selection segments in the workspace describe the repertoire this
+        # workspace belongs to: set by qdx_select_prepare and by every qdx_commit (whose last CTA rescans the
+        # fitness array), so a steady-state generation needs no prepare launch.
+        self.sel_valid = False
+        self.xchg: Optional["PeerExchange"] = None
 
     @property
     def ptr(self) -> C.c_void_p:
@@ -166,6 +171,85 @@ def select_prepare(rep_f: torch.Tensor, ws: Workspace, key_mode: int = KEYMODE_K
     k0, k1 = key_words(key) if key is not None else (0, 0)
     call("qdx_select_prepare", _ptr(rep_f), C.c_int64(rep_f.numel()), ws.ptr, C.c_int32(key_mode), C.c_uint32(k0),
          C.c_uint32(k1), C.c_int32(rank_slot), _stream())
+    ws.sel_valid = True
+
+
+def ensure_selection(rep_f: torch.Tensor, ws: Workspace) -> None:
+    """Occupancy scan + selection segments, only if the last commit has not already left them in the workspace."""
+    if not ws.sel_valid:
+        select_prepare(rep_f, ws, KEYMODE_KEEP)
+
+
+def host_generation_keys(key_mode: int, key=None, carry: Optional[np.ndarray] = None):
+    """The jax.random.split chain of one generation, on the host (a few Threefry blocks): returns the 8 key words
+    {sel1, sel2, line, leaf} as a ctypes array for qdx_generate / qdx_xchg_push.  key_mode KEYMODE_SCAN advances
+    `carry` (uint32[2] NumPy array) in place."""
+    out = (C.c_uint32 * 8)()
+    k0, k1 = key_words(key) if key is not None else (0, 0)
+    cio = (C.c_uint32 * 2)(*(int(x) for x in carry)) if carry is not None else None
+    call("qdx_host_generation_keys", C.c_int32(key_mode), C.c_uint32(k0), C.c_uint32(k1), cio, out)
+    if carry is not None:
+        carry[0], carry[1] = cio[0], cio[1]
+    return out
+
+
+class PeerExchange:
+    """Peer-memory exchange buffers of DistributedMAPElites(exchange="p2p"): this rank's buffer (cudaMalloc, exported
+    with cudaIpc) and the mappings of every peer's buffer.  torch.distributed is used only to hand the 64-byte IPC
+    handles around (all_gather_object) and for the set-up barrier.  `attach(ws)` records the mappings in a workspace;
+    the generation counter lives in the buffer itself, so workspaces may come and go (cloned repertoires)."""
+
+    def __init__(self, K: int, group=None):
+        import torch.distributed as dist
+
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        self.K = K
+        self.local = C.c_void_p(0)
+        handle = (C.c_char * 64)()
+        call("qdx_xchg_create", C.c_int64(K), C.byref(self.local), C.cast(handle, C.c_void_p))
+        handles = [None] * self.size
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peers = (C.c_void_p * self.size)()
+        self._opened = []
+        for q in range(self.size):
+            if q == self.rank:
+                self.peers[q] = self.local.value
+            else:
+                pp = C.c_void_p(0)
+                hb = C.create_string_buffer(handles[q], 64)
+                call("qdx_xchg_open", C.cast(hb, C.c_void_p), C.byref(pp))
+                self.peers[q] = pp.value
+                self._opened.append(pp.value)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)          # every rank's buffer is zeroed and mapped before anybody pushes
+
+    def attach(self, ws: "Workspace") -> None:
+        if ws.xchg is not self:
+            if ws.K != self.K:
+                raise ValueError("exchange buffers were created for a different number of cells")
+            call("qdx_xchg_attach", ws.ptr, C.c_int32(self.rank), C.c_int32(self.size), self.peers, _stream())
+            ws.xchg = self
+
+    def close(self) -> None:
+        if self.local.value:
+            torch.cuda.synchronize()
+            for p in self._opened:
+                call("qdx_xchg_close", C.c_void_p(p))
+            call("qdx_xchg_destroy", self.local)
+            self.local = C.c_void_p(0)
+
+
+def xchg_push(ws: Workspace, gen_keys) -> None:
+    call("qdx_xchg_push", ws.ptr, C.c_int64(ws.K), gen_keys, _stream())
+
+
+def elect_winners(ws: Workspace, rep_g: torch.Tensor, task: str, desc_dim: int, B_dev: int, nranks: int, iso_sigma: float,
+                  line_sigma: float, minval, maxval, first_wins: bool, stage_g, stage_f, stage_d, wait_peers: bool = False) -> None:
+    K, D = rep_g.shape
+    call("qdx_elect_winners", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim), C.c_int64(B_dev),
+         C.c_int32(nranks), _ptr(rep_g), C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None),
+         C.c_float(minval or 0.0), C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(bool(first_wins)),
+         _ptr(stage_g), _ptr(stage_f), _ptr(stage_d), C.c_int32(bool(wait_peers)), _stream())
 
 
 def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: int, iso_sigma: float, line_sigma: float, minval,
@@ -178,13 +262,13 @@ def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: i
 
 def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, line_sigma: float, minval, maxval,
              task: Optional[str], desc_dim: int, grid: Optional[Grid], offer: bool, idx_base: int, first_wins: bool,
-             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None) -> None:
+             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None, gen_keys=None) -> None:
     K, D = rep_g.shape
     call("qdx_generate", _ptr(rep_g), _ptr(rep_f), _ptr(centroids), ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B),
          C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
          C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim),
          _grid_ptr(grid), C.c_int32(bool(offer)), C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _ptr(out_g), _ptr(out_f),
-         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), _stream())
+         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _stream())
 
 
 def score(task: str, g: torch.Tensor, desc_dim: int = 2, out_f: Optional[torch.Tensor] = None,
@@ -259,6 +343,8 @@ def commit(ws: Workspace, off_g, off_f, off_d, rep_g, rep_f, rep_d, idx_base: in
     call("qdx_commit", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int32(rep_d.shape[1]), _ptr(off_g), _ptr(off_f), _ptr(off_d),
          C.c_uint32(idx_base), C.c_int64(off_f.numel()), C.c_int32(bool(first_wins)), _ptr(rep_g), _ptr(rep_f), _ptr(rep_d),
          C.c_float(qd_offset), _ptr(metrics_out), _ptr(added_cells), C.c_int32(mode), _stream())
+    if mode != 1:
+        ws.sel_valid = True     # the last CTA of the commit kernel rescanned rep_f
 
 
 def select_indices(ws: Workspace, key, num: int, device) -> torch.Tensor:

@@ -19,6 +19,8 @@ class PyTreeNode:
             if not hasattr(new, k):
                 raise AttributeError(f"{type(self).__name__} has no field {k!r}")
             object.__setattr__(new, k, v)
+        if "fitnesses" in updates and hasattr(new, "_ws"):
+            object.__setattr__(new, "_ws", None)     # the device workspace describes one fitness array
         return new
 
 

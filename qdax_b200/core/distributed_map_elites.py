@@ -12,6 +12,11 @@ rank * B_dev + i), same per-rank key chain (`key, subkey = split(key)`; emit(sub
                         rank's generation keys in tail slots; every rank then REGENERATES the winners from (owner's
                         keys, local index) -- the RNG is counter-based and the repertoire replicated -- scores them
                         and commits.  No genotype crosses NVLink.
+  exchange="p2p"        the regen exchange without a collective library: every rank max-merges its non-empty key-table
+                        entries and its generation keys straight into every peer's table with system-scope 64-bit
+                        atomicMax over NVLink (buffers mapped with cudaIpc, double-buffered by generation parity) and
+                        raises an arrival flag there; the elect kernel acquire-spins on its local flags, then
+                        regenerates + scores the winners.  generate -> push -> elect -> commit, no host involvement.
   exchange="winners"    only what can change the repertoire travels: each rank offers its shard into its local
                         64-bit key table, one all-reduce(max) of the K keys elects the global per-cell winners
                         (the global best of a cell is always a local best), winners' rows are merged through a
@@ -37,11 +42,12 @@ from qdax_b200.core.map_elites import MAPElites
 class DistributedMAPElites(MAPElites):
     def __init__(self, *args, exchange: str = "allgather", group=None, **kwargs) -> None:
         super().__init__(*args, **kwargs)
-        if exchange not in ("allgather", "winners", "regen"):
-            raise ValueError("exchange must be 'allgather', 'winners' or 'regen'")
+        if exchange not in ("allgather", "winners", "regen", "p2p"):
+            raise ValueError("exchange must be 'allgather', 'winners', 'regen' or 'p2p'")
         self._exchange = exchange
         self._group = group
         self._dist_buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self._xchg: Optional[_native.PeerExchange] = None
 
     # ------------------------------------------------------------------------------------------ reference API
     def init(self, genotypes, centroids, key) -> Tuple[MapElitesRepertoire, Optional[EmitterState], Dict]:
@@ -83,14 +89,25 @@ class DistributedMAPElites(MAPElites):
         rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
         first = rep.tie_break == "first"
-        winners = self._exchange in ("winners", "regen")
+        winners = self._exchange in ("winners", "regen", "p2p")
+        p2p = self._exchange == "p2p" and R > 1
         base = rank * B
+        if p2p:
+            if self._xchg is None or self._xchg.K != K:
+                self._xchg = _native.PeerExchange(K, self._group)
+            self._xchg.attach(ws)
+        gen_keys = _native.host_generation_keys(key_mode, key)
         self._mark("begin")
-        _native.select_prepare(rep_f, ws, key_mode, key, rank_slot=rank if self._exchange == "regen" else -1)
+        if self._exchange == "regen" and R > 1:
+            # the generation keys ride behind the key table in the all-reduce: prepare publishes them (and clears the
+            # other ranks' slots), so this exchange keeps its prepare launch
+            _native.select_prepare(rep_f, ws, key_mode, key, rank_slot=rank)
+        else:
+            _native.ensure_selection(rep_f, ws)
         self._mark("prepare")
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], Dd, grid, winners and grid is not None, base, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"])
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys)
         if grid is None:   # cell assignment stays sharded: each rank assigns only its own offspring
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=winners, idx_base=base, first_wins=first, out=buf["c"])
         self._mark("generate")
@@ -112,11 +129,14 @@ class DistributedMAPElites(MAPElites):
             return
         st = gb["stage"]
         sg, sd, sf = _stage_views(st, D, Dd)
-        if self._exchange == "regen":
-            parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
-            _native.regenerate_winners(ws, rep.genotypes, B, R, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"], cfg["maxval"],
-                                       first, sg)
-            _native.score(cfg["task"], sg, Dd, out_f=sf, out_d=sd)
+        if self._exchange in ("regen", "p2p"):
+            if p2p:
+                _native.xchg_push(ws, gen_keys)
+            else:
+                parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
+            self._mark("exchange_keys")
+            _native.elect_winners(ws, rep.genotypes, cfg["task"], Dd, B, R, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
+                                  cfg["maxval"], first, sg, sf, sd, wait_peers=p2p)
             self._mark("exchange")
             _native.commit(ws, sg, sf, sd, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
                            metrics_out=metrics_out, mode=2)

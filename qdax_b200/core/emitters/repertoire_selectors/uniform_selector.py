@@ -25,7 +25,7 @@ class UniformSelector(Selector):
         if f.dim() == 2 and f.shape[1] != 1:
             raise NotImplementedError("multi-objective fitnesses are outside the MAP-Elites hot path")
         ws = rep._workspace()
-        _native.select_prepare(f.reshape(-1), ws)
+        _native.ensure_selection(f.reshape(-1), ws)
         return _native.select_indices(ws, key, num_samples, f.device)
 
     def select(self, repertoire, key, num_samples: int):

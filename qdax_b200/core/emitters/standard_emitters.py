@@ -60,10 +60,11 @@ class MixingEmitter(Emitter):
                 and (g.numel() // g.shape[0]) % 4 == 0 and repertoire.fitnesses.shape[-1] == 1:
             K = g.shape[0]
             ws = repertoire._workspace()
-            _native.select_prepare(repertoire.fitnesses.reshape(-1), ws, _native.KEYMODE_EMIT, key)
+            _native.ensure_selection(repertoire.fitnesses.reshape(-1), ws)
             out = torch.empty((self._batch_size,) + tuple(g.shape[1:]), dtype=torch.float32, device=g.device)
             _native.generate(g.reshape(K, -1), repertoire.fitnesses.reshape(-1), None, ws, self._batch_size, cfg["iso_sigma"],
-                             cfg["line_sigma"], cfg["minval"], cfg["maxval"], None, 1, None, False, 0, True, out, None, None)
+                             cfg["line_sigma"], cfg["minval"], cfg["maxval"], None, 1, None, False, 0, True, out, None, None,
+                             gen_keys=_native.host_generation_keys(_native.KEYMODE_EMIT, key))
             return out, {}
 
         n_variation = int(self._batch_size * self._variation_percentage)

@@ -103,8 +103,11 @@ class MAPElites:
             e.record()
             self._timeline.append((label, e))
 
-    def _fused_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out: torch.Tensor) -> None:
-        """One generation in place on `rep` (launch-only; no host synchronisation)."""
+    def _fused_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out: torch.Tensor,
+                          carry: Optional[np.ndarray] = None) -> None:
+        """One generation in place on `rep` (launch-only; no host synchronisation).  Steady state = two launches:
+        generate (select + variation + scoring + cell + offer) and commit (whose last CTA also leaves the next
+        generation's parent-selection tables in the workspace); the jax.random.split chain runs on the host."""
         K, D = rep.genotypes.shape
         B = self._emitter.batch_size
         buf = self._offspring_buffers(B, D, cfg["desc_dim"], rep.genotypes.device)
@@ -112,12 +115,13 @@ class MAPElites:
         rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
         first = rep.tie_break == "first"
+        gen_keys = _native.host_generation_keys(key_mode, key, carry)
         self._mark("begin")
-        _native.select_prepare(rep_f, ws, key_mode, key)
+        _native.ensure_selection(rep_f, ws)
         self._mark("prepare")
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], cfg["desc_dim"], grid, grid is not None, 0, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"])
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys)
         self._mark("generate")
         if grid is None:
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=True, first_wins=first, out=buf["c"])
@@ -199,25 +203,26 @@ class MAPElites:
             return (repertoire, emitter_state, key), stacked
         rep = repertoire if donate else repertoire._clone_state()
         ws = rep._workspace()
-        ws.set_carry_key(key)
+        carry = np.array(_native.key_words(key), dtype=np.uint32)      # the scan carry key, advanced on the host (:214)
         metrics = torch.empty((length, 4), dtype=torch.float32, device=rep.genotypes.device)
         if graph and length > 0:
             # warm-up outside the capture (module load, offspring buffers) on a throw-away copy of the state
-            self._fused_generation(repertoire._clone_state(), cfg, _native.KEYMODE_KEEP, None, metrics[0])
+            self._fused_generation(repertoire._clone_state(), cfg, _native.KEYMODE_SCAN, None, metrics[0], carry.copy())
+            _native.ensure_selection(rep.fitnesses.reshape(-1), ws)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for it in range(length):
-                    self._fused_generation(rep, cfg, _native.KEYMODE_SCAN, None, metrics[it])
+                    self._fused_generation(rep, cfg, _native.KEYMODE_SCAN, None, metrics[it], carry)
             g.replay()
         else:
             for it in range(length):
-                self._fused_generation(rep, cfg, _native.KEYMODE_SCAN, None, metrics[it])
-        carry_key, _, err = ws.read()
+                self._fused_generation(rep, cfg, _native.KEYMODE_SCAN, None, metrics[it], carry)
+        _, _, err = ws.read()
         if err != 0:
             from .._lib import QdxError
             raise QdxError("MAPElites.scan", err)
-        return (rep, emitter_state, carry_key), self._metrics_dict(metrics)
+        return (rep, emitter_state, carry), self._metrics_dict(metrics)
 
     def ask(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key):
         """reference :227-243."""

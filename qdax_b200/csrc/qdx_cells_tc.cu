@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             // non-finite descriptor: every distance is inf or NaN -> first index (centroids are finite)
             if (resolved) {
                 p.cells[row] = cell;
-                if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
+                if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
             } else {
                 const int slot = atomicAdd(p.fallback_count, 1);
                 p.fallback_rows[slot] = (int32_t)row;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(128) qdx_cells_tc_fallback_kernel(const QdxTcP
         if (lane == 0) {
             const int32_t cell = bk == 0x7fffffff ? 0 : (int32_t)bk;
             p.cells[row] = cell;
-            if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
+            if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
         }
     }
 }

@@ -23,6 +23,7 @@ struct QdxGenKeys {
 };
 
 #define QDX_MAX_COMMIT_CTAS (148 * 8)
+#define QDX_MAX_PEERS 16      // ranks of one NVLink domain whose key tables are mapped into each other (cudaIpc)
 
 // Device workspace header (one per repertoire); arrays follow at fixed offsets (qdx_ws_* below).
 struct QdxWorkspace {
@@ -32,13 +33,19 @@ struct QdxWorkspace {
     float metrics[4];       // qd_score, max_fitness, coverage, num_added
     uint32_t ticket;        // last-CTA-done counter of the commit kernel
     int32_t error;          // sticky device-side error flag (e.g. empty repertoire)
-    uint32_t pad[2];
+    uint32_t push_ticket;   // last-CTA-done counter of the peer-memory push kernel
+    uint32_t pad0;
+    // ---- peer-memory exchange (multi-GPU, one process per GPU; qdx_xchg_* in include/qdx.h); 0 = not attached
+    unsigned long long xchg_peer[QDX_MAX_PEERS];   // exchange buffer of every rank as mapped into THIS process
+    int32_t xchg_rank;
+    int32_t xchg_nranks;
     // per-CTA partial metrics of the commit kernel, summed in CTA order by the last CTA (deterministic)
     double part_sum[QDX_MAX_COMMIT_CTAS];
     float part_max[QDX_MAX_COMMIT_CTAS];
     int32_t part_cnt[QDX_MAX_COMMIT_CTAS];
     int32_t part_add[QDX_MAX_COMMIT_CTAS];
     int32_t part_nan[QDX_MAX_COMMIT_CTAS];
+    int32_t part_new[QDX_MAX_COMMIT_CTAS];      // cells that turned from empty to occupied in this commit
 };
 
 __host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -51,8 +58,27 @@ __host__ __device__ inline size_t qdx_ws_total_bytes(int64_t K) {
     return qdx_align_up(qdx_ws_keytab_offset(K) + sizeof(unsigned long long) * (size_t)(K + 8 * QDX_MAX_RANKS), 256);
 }
 __host__ __device__ inline int32_t* qdx_ws_occ(void* ws) { return (int32_t*)((char*)ws + qdx_ws_occ_offset()); }
-__host__ __device__ inline unsigned long long* qdx_ws_keytab(void* ws, int64_t K) {
-    return (unsigned long long*)((char*)ws + qdx_ws_keytab_offset(K));
+// Peer-memory exchange buffer of one rank (cudaMalloc'ed by qdx_xchg_create, mapped into every peer with cudaIpc):
+//   [0, 512)             arrival flags: flag[r] = epoch + 1 once rank r's keys of that epoch have landed here
+//   [512, 516)           epoch: generation counter of this rank (advanced by the commit kernel; lives here rather than in
+//                        the workspace so that it survives when a cloned repertoire brings a fresh workspace)
+//   then 2 key tables    (K keys + 8 * QDX_MAX_RANKS generation-key slots) x uint64, selected by epoch parity so a
+//                        fast rank may push generation e+1 while this rank still consumes generation e
+__host__ __device__ inline size_t qdx_xchg_tab_entries(int64_t K) { return (size_t)K + 8 * QDX_MAX_RANKS; }
+__host__ __device__ inline size_t qdx_xchg_tab_offset(int64_t K, int parity) {
+    return 1024 + (size_t)parity * qdx_align_up(qdx_xchg_tab_entries(K) * sizeof(unsigned long long), 256);
+}
+__host__ __device__ inline size_t qdx_xchg_total_bytes(int64_t K) { return qdx_xchg_tab_offset(K, 2); }
+#define QDX_XCHG_EPOCH_OFFSET 512
+// The insertion key table of the current generation: inside the workspace on one GPU, inside the exchange buffer
+// (parity of the epoch) when the peer-memory exchange is attached.
+__device__ __forceinline__ unsigned long long* qdx_ws_keytab(void* ws_raw, int64_t K) {
+    const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
+    if (ws->xchg_nranks > 0) {
+        char* base = (char*)ws->xchg_peer[ws->xchg_rank];
+        return (unsigned long long*)(base + qdx_xchg_tab_offset(K, (int)(*(const uint32_t*)(base + QDX_XCHG_EPOCH_OFFSET) & 1u)));
+    }
+    return (unsigned long long*)((char*)ws_raw + qdx_ws_keytab_offset(K));
 }
 
 // Separable ("Euclidean grid") tessellation: centroid of cell sum_d idx_d*stride_d is (axis_0[idx_0], ...).
@@ -81,7 +107,13 @@ QDX_DEV uint32_t qdx_key_index(unsigned long long key, int first_wins) {
 // Offer offspring `idx` with fitness f to cell c (MapElitesRepertoire.add, mapelites_repertoire.py:211-231):
 // only candidates that can change the outcome touch the table (NaN poisons its cell; f <= current never wins
 // and never blocks a winner because any winner has f > current >= f).
-QDX_DEV void qdx_offer(unsigned long long* keytab, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
+// With the peer-memory exchange attached, peers push into the same table with system-scope atomics while this rank
+// may still be offering, so the local atomics are system scope too (same L2 operation on local memory).
+QDX_DEV void qdx_offer(void* ws, int64_t K, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
     const float cur = __ldg(rep_f + c);
-    if ((f != f) || f > cur) atomicMax(keytab + c, qdx_pack_key(f, idx, first_wins));
+    if ((f != f) || f > cur) {
+        unsigned long long* slot = qdx_ws_keytab(ws, K) + c;
+        const unsigned long long key = qdx_pack_key(f, idx, first_wins);
+        if (((const QdxWorkspace*)ws)->xchg_nranks > 0) atomicMax_system(slot, key); else atomicMax(slot, key);
+    }
 }

@@ -33,15 +33,81 @@ __device__ void qdx_derive_gen_keys(QdxKey emit, QdxGenKeys* out) {
     out->leaf = qdx_split(qdx_split(kv, 0), 0);                                          // :220 (one leaf)
 }
 
+// Occupancy scan by ONE CTA (any multiple of 32 threads, <= 1024): ordered list of occupied cells -> occ[], M, and the
+// selection segments (rebuilt only when M changed).  Warp w owns the contiguous cell range [w*chunk, (w+1)*chunk);
+// 32 cells per step, ballot + popc, every load coalesced and independent of the previous step.  Used by the
+// prepare kernel and by the last CTA of the commit kernel (which leaves the NEXT generation's selection ready, so a
+// steady-state generation needs no prepare launch).  s_warp: >= 33 int32 of shared memory.
+__device__ void qdx_cta_occupancy_scan(const float* rep_f, int64_t K, void* ws_raw, int32_t* s_warp) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    int32_t* occ = qdx_ws_occ(ws_raw);
+    constexpr int BAL = 2048;                       // ballot words kept in shared memory: K <= 65536 needs no second read
+    __shared__ uint32_t s_bal[BAL];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+    const int64_t chunk = ((K + nw - 1) / nw + 31) / 32 * 32;
+    const int64_t lo = (int64_t)w * chunk, hi = lo + chunk < K ? lo + chunk : K;
+    const bool keep = (K + 31) / 32 <= BAL;
+    // every step's load is independent of the previous step's ballot: 16 loads in flight per lane (the fitness array is
+    // L2-resident, so the scan is latency- not bandwidth-bound)
+    constexpr int U = 16;
+    int32_t cnt = 0;
+    for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned b = __ballot_sync(0xffffffffu, v[u] != -INFINITY);
+            cnt += __popc(b);
+            if (keep && lane == 0 && c0 + 32 * u < hi) s_bal[(c0 >> 5) + u] = b;
+        }
+    }
+    __syncthreads();                       // s_warp may still be in use by the caller
+    if (lane == 0) s_warp[w] = cnt;
+    __syncthreads();
+    if (w == 0) {
+        int32_t v = lane < nw ? s_warp[lane] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        __syncwarp();
+        s_warp[lane] = x - v;
+        if (lane == 31) s_warp[32] = x;
+    }
+    __syncthreads();
+    int32_t pos = s_warp[w];
+    if (keep) {
+        for (int64_t c0 = lo; c0 < hi; c0 += 32) {
+            const unsigned b = s_bal[c0 >> 5];
+            if ((b >> lane) & 1u) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + lane);
+            pos += __popc(b);
+        }
+    } else {
+        for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool o = v[u] != -INFINITY;
+                const unsigned b = __ballot_sync(0xffffffffu, o);
+                if (o) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + 32 * u + lane);
+                pos += __popc(b);
+            }
+        }
+    }
+    if (t == 0) {
+        const int32_t M = s_warp[32];
+        if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
+    }
+}
+
 // key_mode: 0 keep keys; 1 `key` = key of MAPElites.update; 2 scan step on ws->carry; 3 `key` = key of
 // DistributedMAPElites.update; 4 `key` = emit key.
 __global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restrict__ rep_f, int64_t K, void* ws_raw,
                                                            QdxKey key, int key_mode, int rank_slot) {
     QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
-    int32_t* occ = qdx_ws_occ(ws_raw);
-    __shared__ int32_t s_warp[32];
-    __shared__ int32_t s_total;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    __shared__ int32_t s_warp[33];
+    const int t = threadIdx.x;
 
     if (rank_slot >= 0) {     // the other ranks' key slots must be empty before the all-reduce(max) fills them
         unsigned long long* slots = qdx_ws_keytab(ws_raw, K) + K;
@@ -61,30 +127,8 @@ __global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restri
         }
     }
 
-    const int64_t chunk = (K + blockDim.x - 1) / blockDim.x;
-    const int64_t lo = (int64_t)t * chunk, hi = lo + chunk < K ? lo + chunk : K;
-    int32_t cnt = 0;
-    for (int64_t c = lo; c < hi; ++c) cnt += (rep_f[c] != -INFINITY);
-    int32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        int32_t v = s_warp[lane], x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        s_warp[lane] = x - v;
-        if (lane == 31) s_total = x;
-    }
-    __syncthreads();
-    int32_t pos = s_warp[w] + incl - cnt;
-    for (int64_t c = lo; c < hi; ++c) if (rep_f[c] != -INFINITY) occ[pos++] = (int32_t)c;
-    if (t == 0) {
-        const int32_t M = s_total;
-        if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
-        if (M <= 0 || ws->sel.nseg <= 0) ws->error = QDX_ERR_EMPTY_REPERTOIRE;
-    }
+    qdx_cta_occupancy_scan(rep_f, K, ws_raw, s_warp);
+    if (t == 0 && (ws->sel.M <= 0 || ws->sel.nseg <= 0)) ws->error = QDX_ERR_EMPTY_REPERTOIRE;
 }
 
 // =====================================================================================================
@@ -154,6 +198,7 @@ struct QdxGenParams {
     int32_t desc_dim;
     QdxGrid grid;
     int32_t offer; uint32_t idx_base; int32_t first_wins;
+    int32_t keys_by_value; QdxGenKeys keys;          // generation keys derived on the host (qdx_host_generation_keys)
 };
 
 QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
@@ -179,7 +224,10 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
     if (GRID_DD > 0) for (int i = threadIdx.x; i < p.grid.total_axes; i += blockDim.x) s_axes[i] = p.grid.axes[i];
     __syncthreads();
-    if (nseg <= 0) return;     // empty repertoire: error flag already raised by prepare
+    if (nseg <= 0) {           // empty repertoire: p = 0/0 in the reference (uniform_selector.py:45)
+        if (blockIdx.x == 0 && threadIdx.x == 0) ((QdxWorkspace*)p.ws)->error = QDX_ERR_EMPTY_REPERTOIRE;
+        return;
+    }
 
     float* tile = s_tiles + (size_t)warp * 32 * DS;
     const int64_t row0 = ((int64_t)blockIdx.x * QDX_GEN_WARPS + warp) * 32;
@@ -187,7 +235,7 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
     const int64_t row = row0 + lane;
     const bool valid = row < p.B;
     const int nrows = (p.B - row0) < 32 ? (int)(p.B - row0) : 32;
-    const QdxGenKeys keys = ws->keys;
+    const QdxGenKeys keys = p.keys_by_value ? p.keys : ws->keys;
     const int32_t* __restrict__ occ = qdx_ws_occ(p.ws);
     const float total = ws->sel.total;
 
@@ -228,10 +276,19 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
             const float4 a = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pa * D + d));
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.rep_g + (int64_t)pb * D + d));
             const uint64_t ctr = (uint64_t)(row0 + rr) * (uint64_t)D + (uint64_t)d;
-            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, xv[4];
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, xv[4], nz[4];
+#ifdef QDX_GEN_SERIAL_NORMALS      // A/B switch (profiles/r1_notes.md): one serial chain + one branch per draw
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nz[j] = qdx_normal_from_bits_t<true>(qdx_bits32(keys.leaf, ctr + j));
+#else
+            uint32_t bits[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bits[j] = qdx_bits32(keys.leaf, ctr + j);     // four independent Threefry chains
+            qdx_normal4_from_bits(bits, nz);
+#endif
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float iso = qdx_normal_from_bits_t<true>(qdx_bits32(keys.leaf, ctr + j)) * p.iso_sigma;
+                float iso = nz[j] * p.iso_sigma;
                 float t1 = av[j] + iso;
                 float t2 = bv[j] - av[j];
                 float t3 = t2 * ln;
@@ -298,7 +355,7 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
                     float xd[QDX_MAX_GRID_DIM] = {dx, dy, 0.0f, 0.0f};
                     const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
                     if (p.out_cell) p.out_cell[row] = cell;
-                    if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                    if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
                 }
             } else {
                 for (int d = 0; d < dc; d += 4) {
@@ -332,7 +389,7 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
                         for (int j = 0; j < (GRID_DD == 0 ? 1 : GRID_DD); ++j) xd[j] = p.out_d[row * p.desc_dim + j];
                         const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
                         if (p.out_cell) p.out_cell[row] = cell;
-                        if (p.offer) qdx_offer(qdx_ws_keytab(p.ws, p.K), p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                        if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
                     }
                 }
             }
@@ -465,7 +522,7 @@ __global__ void __launch_bounds__(256) qdx_cells_bf_kernel(const float* __restri
     if (!valid) return;
     // non-finite descriptor: every distance is inf or NaN -> argmin = 0 (first inf / first NaN), centroids finite
     cells[row] = bk;
-    if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, bk, fit[row], idx_base + (uint32_t)row, first_wins);
+    if (offer) qdx_offer(ws, K, rep_f, bk, fit[row], idx_base + (uint32_t)row, first_wins);
 }
 
 // generic descriptor dimension (runtime Dd): same algorithm, descriptor row kept in shared memory
@@ -498,7 +555,7 @@ __global__ void __launch_bounds__(128) qdx_cells_bf_generic_kernel(const float* 
     if (lane == 0) {
         int32_t cell = (nan_k != 0x7fffffff) ? (int32_t)nan_k : (bk == 0x7fffffff ? 0 : (int32_t)bk);
         cells[row] = cell;
-        if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
+        if (offer) qdx_offer(ws, K, rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
     }
 }
 
@@ -519,7 +576,7 @@ __global__ void __launch_bounds__(256) qdx_cells_grid_kernel(const float* __rest
     for (int d = 0; d < DD; ++d) x[d] = desc[row * DD + d];
     const int32_t cell = qdx_grid_cell<DD>(x, grid, s_axes, cent, K);
     cells[row] = cell;
-    if (offer) qdx_offer(qdx_ws_keytab(ws, K), rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
+    if (offer) qdx_offer(ws, K, rep_f, cell, fit[row], idx_base + (uint32_t)row, first_wins);
 }
 
 // offer only: cells already known (tell / add with injected cells, or after an all-gather)
@@ -530,7 +587,7 @@ __global__ void __launch_bounds__(256) qdx_offer_kernel(const int32_t* __restric
     if (row >= B) return;
     const int32_t c = cells[row];
     if (c < 0 || c >= K) { ((QdxWorkspace*)ws)->error = QDX_ERR_BAD_CELL; return; }
-    qdx_offer(qdx_ws_keytab(ws, K), rep_f, c, fit[row], idx_base + (uint32_t)row, first_wins);
+    qdx_offer(ws, K, rep_f, c, fit[row], idx_base + (uint32_t)row, first_wins);
 }
 
 // =====================================================================================================
@@ -552,7 +609,7 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int added = 0;
+    int added = 0, newly = 0;
     double sum = 0.0; float mx = -INFINITY; int cnt = 0; int nan = 0;      // metrics of this warp's cells (lane 0)
     // One warp per CELL (grid-stride): every resident warp has a winner row in flight, which is what lets the row
     // traffic approach the HBM roofline when rows are large (K/32-warp parallelism measured 35 % of peak).
@@ -584,7 +641,11 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
             }
             for (int d = lane; d < Dd; d += 32) rep_d[cell * Dd + d] = off_d[i * Dd + d];
             fcell = off_f[i];
-            if (lane == 0) { rep_f[cell] = fcell; if (added_cells) added_cells[cell] = (int32_t)i; }
+            if (lane == 0) {
+                if (__ldcg(rep_f + cell) == -INFINITY) ++newly;     // the occupied-cell list changes: rescan at the end
+                rep_f[cell] = fcell;
+                if (added_cells) added_cells[cell] = (int32_t)i;
+            }
             ++added;
         } else {
             fcell = (mode == 1) ? -INFINITY : __ldcg(rep_f + cell);
@@ -596,15 +657,16 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     // ---- metrics: CTAs publish partials of their cells, the last CTA to finish sums them in CTA order (deterministic)
     if (mode == 1) return;
     __shared__ double s_sum[8]; __shared__ float s_max[8]; __shared__ int s_cnt[8]; __shared__ int s_nan[8]; __shared__ int s_add[8];
+    __shared__ int s_new[8];
     __shared__ bool s_last;
     const int wid = threadIdx.x >> 5;
-    if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; }
+    if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; s_new[wid] = newly; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; }
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0, nw = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; nw += s_new[w]; }
         ws->part_sum[blockIdx.x] = s; ws->part_max[blockIdx.x] = m; ws->part_cnt[blockIdx.x] = n; ws->part_nan[blockIdx.x] = nn;
-        ws->part_add[blockIdx.x] = a;
+        ws->part_add[blockIdx.x] = a; ws->part_new[blockIdx.x] = nw;
         __threadfence();
         const unsigned t = atomicAdd(&ws->ticket, 1u);
         s_last = (t == gridDim.x - 1);
@@ -614,17 +676,19 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     __threadfence();
     // fixed-shape reduction of the per-CTA partials: thread t sums partials t, t+256, ... then warps, then thread 0
     {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0, nw = 0;
         for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
             s += *(volatile double*)&ws->part_sum[b]; m = fmaxf(m, *(volatile float*)&ws->part_max[b]);
             n += *(volatile int32_t*)&ws->part_cnt[b]; nn |= *(volatile int32_t*)&ws->part_nan[b]; a += *(volatile int32_t*)&ws->part_add[b];
+            nw += *(volatile int32_t*)&ws->part_new[b];
         }
         for (int o = 16; o > 0; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             n += __shfl_xor_sync(0xffffffffu, n, o); nn |= __shfl_xor_sync(0xffffffffu, nn, o); a += __shfl_xor_sync(0xffffffffu, a, o);
+            nw += __shfl_xor_sync(0xffffffffu, nw, o);
         }
         __syncthreads();
-        if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; }
+        if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; s_new[wid] = nw; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -637,23 +701,101 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
         out[3] = (float)a;                                         // offspring inserted by this call
         for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (metrics_out) metrics_out[j] = out[j]; }
         ws->ticket = 0u;
+        if (mode == 2 && ws->xchg_nranks > 0) {                              // next generation: the other key table
+            uint32_t* ep = (uint32_t*)((char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET);
+            *ep = *ep + 1u;
+        }
     }
+    // ---- the repertoire is final: leave the NEXT generation's parent selection ready (no prepare launch).  The
+    // occupied-cell list only changes when a cell turned from empty to occupied (never in steady state), or when the
+    // workspace has not seen this repertoire yet (M mismatch: e.g. first commit after init).
+    __shared__ int32_t s_scan[33];
+    int total_new = 0, total_cnt = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { total_new += s_new[w]; total_cnt += s_cnt[w]; }
+    if (total_new != 0 || total_cnt != ws->sel.M || ws->sel.nseg <= 0) qdx_cta_occupancy_scan(rep_f, K, ws_raw, s_scan);
 }
 
 // =====================================================================================================
-// regenerate the elected winners (multi-GPU "regen" exchange)
+// peer-memory exchange (multi-GPU): push the local per-cell bests into every peer's key table over NVLink
 // =====================================================================================================
-// After the all-reduce(max) of the key table every rank knows, per cell, the global index of the winning offspring
-// and (tail slots) every rank's generation keys.  The RNG is counter-based and the repertoire is replicated, so the
-// winner's genotype is recomputed locally, bit for bit as its owner produced it, into a per-cell staging row -- no
-// genotype crosses NVLink.  One warp per elected cell.
-__global__ void __launch_bounds__(256) qdx_regen_kernel(void* ws_raw, int64_t K, int32_t D, int64_t B_dev, int32_t nranks,
-                                                        const float* __restrict__ rep_g, float iso_sigma, float line_sigma,
-                                                        int32_t has_min, float minv, int32_t has_max, float maxv,
-                                                        int32_t first_wins, float* __restrict__ stage_g) {
+// DistributedMAPElites (distributed_map_elites.py:133-146) needs, per cell, the best offspring over ALL ranks.  Every
+// rank has already reduced its shard into its own key table (atomicMax offers of the generate / cells kernels); the
+// global best of a cell is always some rank's local best, so it is enough to max-merge the (few) non-empty entries
+// into every peer: system-scope 64-bit atomicMax straight into the peer's HBM (mapped with cudaIpc, NVLink 5 /
+// NVSwitch), no staging, no collective library.  The last CTA then publishes "rank `me`, epoch e has landed" in every
+// peer's flag array (release, system scope); consumers acquire-spin on their LOCAL flags (qdx_elect_kernel).
+QDX_DEV void qdx_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+QDX_DEV unsigned long long qdx_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) qdx_push_kernel(void* ws_raw, int64_t K, const QdxGenKeys keys) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    const int R = ws->xchg_nranks, me = ws->xchg_rank;
+    const uint32_t epoch = *(const uint32_t*)((const char*)ws->xchg_peer[me] + QDX_XCHG_EPOCH_OFFSET);
+    const size_t tab_off = qdx_xchg_tab_offset(K, (int)(epoch & 1u));
+    __shared__ unsigned long long* s_tab[QDX_MAX_PEERS];
+    __shared__ bool s_last;
+    if (threadIdx.x < R) s_tab[threadIdx.x] = (unsigned long long*)((char*)ws->xchg_peer[threadIdx.x] + tab_off);
+    __syncthreads();
+    // this rank's generation keys -> slot `me` of every rank's table (disjoint slots, plain stores): the winners are
+    // REGENERATED by every rank from (owner's keys, local index), so no genotype crosses NVLink
+    if (blockIdx.x == 0 && threadIdx.x < 8 * R) {
+        const int q = threadIdx.x >> 3, j = threadIdx.x & 7;
+        const uint32_t w[8] = {keys.sel1.a, keys.sel1.b, keys.sel2.a, keys.sel2.b, keys.line.a, keys.line.b, keys.leaf.a, keys.leaf.b};
+        s_tab[q][K + 8 * me + j] = (unsigned long long)w[j];
+    }
+    const unsigned long long* local = s_tab[me];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < K; c += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = __ldcg(local + c);
+        if (key != 0ull)
+            for (int q = 0; q < R; ++q) if (q != me) atomicMax_system(s_tab[q] + c, key);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ws->push_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x < R)
+        qdx_st_release_sys((unsigned long long*)ws->xchg_peer[threadIdx.x] + me, (unsigned long long)(epoch + 1u));
+    if (threadIdx.x == 0) ws->push_ticket = 0u;
+}
+
+// =====================================================================================================
+// elect: regenerate + score the elected winners (multi-GPU "regen" / "p2p" exchanges)
+// =====================================================================================================
+// After the key tables have been max-merged (NCCL all-reduce, or the peer-memory push above) every rank knows, per
+// cell, the global index of the winning offspring and (tail slots) every rank's generation keys.  The RNG is
+// counter-based and the repertoire replicated, so each rank recomputes the winner's genotype bit for bit as its owner
+// produced it, scores it, and leaves (genotype, fitness, descriptor) in per-cell staging rows for qdx_commit(mode 2).
+// One warp per elected cell.  Scoring keeps the spec's sequential float32 sums (lane 0) but spreads the independent
+// per-gene work (sincos, rastrigin terms) over the 32 lanes.
+template <int TASK>
+__global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K, int32_t D, int32_t desc_dim, int64_t B_dev,
+                                                        int32_t nranks, const float* __restrict__ rep_g, float iso_sigma,
+                                                        float line_sigma, int32_t has_min, float minv, int32_t has_max,
+                                                        float maxv, int32_t first_wins, float* __restrict__ stage_g,
+                                                        float* __restrict__ stage_f, float* __restrict__ stage_d,
+                                                        int32_t wait_peers) {
     __shared__ QdxSeg s_seg[QDX_MAX_SEG];
     __shared__ float s_last[QDX_MAX_SEG];
-    const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
+    __shared__ float s_buf[8][3][128];
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    if (wait_peers && threadIdx.x < ws->xchg_nranks) {     // acquire-spin on the LOCAL arrival flags (bounded: 2 s)
+        const unsigned long long* flag = (const unsigned long long*)ws->xchg_peer[ws->xchg_rank] + threadIdx.x;
+        const uint32_t want = *(const uint32_t*)((const char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET) + 1u;
+        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)((uint32_t)qdx_ld_acquire_sys(flag) - want) < 0) {
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_PEER_TIMEOUT; break; }
+            __nanosleep(64);
+        }
+    }
     const int nseg = ws->sel.nseg;
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
     __syncthreads();
@@ -661,30 +803,80 @@ __global__ void __launch_bounds__(256) qdx_regen_kernel(void* ws_raw, int64_t K,
     const unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
     const int32_t* __restrict__ occ = qdx_ws_occ(ws_raw);
     const float total = ws->sel.total;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* s_x = s_buf[wid][0]; float* s_a = s_buf[wid][1]; float* s_b = s_buf[wid][2];
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp_global; c < K; c += nwarps) {
-        const unsigned long long key = keytab[c];
+        const unsigned long long key = __ldcg(keytab + c);
         if (key == 0ull || qdx_key_is_nan(key)) continue;
         const uint32_t idx = qdx_key_index(key, first_wins);
         const int64_t r = idx / B_dev, i = idx % B_dev;
         if (r >= nranks) continue;
         const unsigned long long* slot = keytab + K + 8 * r;
-        const QdxKey sel1{(uint32_t)slot[0], (uint32_t)slot[1]}, sel2{(uint32_t)slot[2], (uint32_t)slot[3]};
-        const QdxKey kline{(uint32_t)slot[4], (uint32_t)slot[5]}, kleaf{(uint32_t)slot[6], (uint32_t)slot[7]};
+        const QdxKey sel1{(uint32_t)__ldcg(slot + 0), (uint32_t)__ldcg(slot + 1)}, sel2{(uint32_t)__ldcg(slot + 2), (uint32_t)__ldcg(slot + 3)};
+        const QdxKey kline{(uint32_t)__ldcg(slot + 4), (uint32_t)__ldcg(slot + 5)}, kleaf{(uint32_t)__ldcg(slot + 6), (uint32_t)__ldcg(slot + 7)};
         const float u1 = qdx_unit_float(qdx_bits32(sel1, (uint64_t)i)), u2 = qdx_unit_float(qdx_bits32(sel2, (uint64_t)i));
         const int32_t p1 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u1)) - 1];
         const int32_t p2 = occ[qdx_sel_rank(s_seg, s_last, nseg, total * (1.0f - u2)) - 1];
         const float ln = qdx_normal_from_bits(qdx_bits32(kline, (uint64_t)i)) * line_sigma;
-        for (int d = lane; d < D; d += 32) {
-            const float a = __ldg(rep_g + (int64_t)p1 * D + d), b = __ldg(rep_g + (int64_t)p2 * D + d);
-            const float iso = qdx_normal_from_bits(qdx_bits32(kleaf, (uint64_t)i * (uint64_t)D + (uint64_t)d)) * iso_sigma;
-            float t1 = a + iso, t2 = b - a, t3 = t2 * ln;
-            float x = t1 + t3;
-            if (has_min) x = qdx_max_nanprop(x, minv);
-            if (has_max) x = qdx_min_nanprop(x, maxv);
-            stage_g[c * D + d] = x;
+        float acc = 0.0f;                                   // rastrigin / sphere running sum (lane 0)
+        for (int d0 = 0; d0 < D; d0 += 128) {
+            const int dc = (D - d0) < 128 ? (D - d0) : 128;
+            __syncwarp();
+            for (int d = lane; d < dc; d += 32) {
+                const int dg = d0 + d;
+                const float a = __ldg(rep_g + (int64_t)p1 * D + dg), b = __ldg(rep_g + (int64_t)p2 * D + dg);
+                const float iso = qdx_normal_from_bits(qdx_bits32(kleaf, (uint64_t)i * (uint64_t)D + (uint64_t)dg)) * iso_sigma;
+                float t1 = a + iso, t2 = b - a, t3 = t2 * ln;
+                float x = t1 + t3;                                  // mutation_operators.py:211
+                if (has_min) x = qdx_max_nanprop(x, minv);
+                if (has_max) x = qdx_min_nanprop(x, maxv);
+                stage_g[c * D + dg] = x;
+                s_x[d] = x;
+            }
+            __syncwarp();
+            if (TASK == QDX_TASK_ARM) {                 // arm.py:27-44; D <= 128 guaranteed by the launcher
+                float mean = 0.0f;
+                if (lane == 0) {
+                    float sum = 0.0f;
+                    for (int d = 0; d < dc; ++d) sum = sum + qdx_min_nanprop(qdx_max_nanprop(s_x[d], 0.0f), 1.0f);
+                    mean = __fdiv_rn(sum, (float)D);
+                    float sq = 0.0f, th = 0.0f;
+                    for (int d = 0; d < dc; ++d) {
+                        const float x = qdx_min_nanprop(qdx_max_nanprop(s_x[d], 0.0f), 1.0f);
+                        const float dev = x - mean;
+                        sq = sq + dev * dev;
+                        th = th + (0x1.921fb6p+2f * x - 0x1.921fb6p+1f);
+                        s_a[d] = th;
+                    }
+                    stage_f[c] = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
+                }
+                __syncwarp();
+                for (int d = lane; d < dc; d += 32) { float sn, cs; qdx_sincosf(s_a[d], sn, cs); s_a[d] = cs; s_b[d] = sn; }
+                __syncwarp();
+                if (lane == 0) {
+                    float cs = 0.0f, sn = 0.0f;
+                    for (int d = 0; d < dc; ++d) { cs = cs + s_a[d]; sn = sn + s_b[d]; }
+                    stage_d[c * 2 + 0] = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
+                    stage_d[c * 2 + 1] = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
+                }
+            } else if (TASK != QDX_TASK_NONE) {         // standard_functions.py:9-48
+                for (int d = lane; d < dc; d += 32) {
+                    const float x = s_x[d] * 10.0f - 5.0f;
+                    float term = x * x;
+                    if (TASK == QDX_TASK_RASTRIGIN) { float sn, cs; qdx_sincosf(0x1.921fb6p+2f * x, sn, cs); term = term - 10.0f * cs; }
+                    s_a[d] = term;
+                    if (d0 + d < desc_dim) stage_d[c * desc_dim + d0 + d] = s_x[d];
+                }
+                __syncwarp();
+                if (lane == 0) for (int d = 0; d < dc; ++d) acc = acc + s_a[d];
+            }
+        }
+        if (TASK != QDX_TASK_ARM && TASK != QDX_TASK_NONE && lane == 0) {
+            float f = acc;
+            if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
+            stage_f[c] = -f;
         }
     }
 }
@@ -702,7 +894,10 @@ __global__ void __launch_bounds__(256) qdx_select_kernel(void* ws_raw, QdxKey ke
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num) return;
-    if (nseg <= 0) { out[i] = 0; return; }     // empty repertoire: error flag raised by prepare; keep indices in range
+    if (nseg <= 0) {                           // empty repertoire (p = 0/0 in the reference): flag it, keep indices in range
+        if (i == 0) ((QdxWorkspace*)ws_raw)->error = QDX_ERR_EMPTY_REPERTOIRE;
+        out[i] = 0; return;
+    }
     const QdxKey sub = qdx_split(key, 1);
     const float u = qdx_unit_float(qdx_bits32(sub, (uint64_t)i));
     out[i] = qdx_ws_occ(ws_raw)[qdx_sel_rank(s_seg, s_last, nseg, ws->sel.total * (1.0f - u)) - 1];
@@ -783,6 +978,21 @@ __global__ void __launch_bounds__(256) qdx_metrics_kernel(const float* __restric
 // C ABI
 // =====================================================================================================
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+
+// ---- host-side key chain (control plane: a handful of Threefry blocks per generation, no device work) ----
+static inline uint32_t h_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static void h_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* o0, uint32_t* o1) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    static const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+    for (int g = 0; g < 5; ++g) {
+        for (int j = 0; j < 4; ++j) { x0 += x1; x1 = h_rotl(x1, rot[g & 1][j]); x1 ^= x0; }
+        x0 += ks[(g + 1) % 3]; x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    *o0 = x0; *o1 = x1;
+}
+static inline QdxKey h_split(QdxKey k, uint32_t i) { QdxKey o; h_threefry2x32(k.a, k.b, 0u, i, &o.a, &o.b); return o; }
+
 
 static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
     memset(g, 0, sizeof(*g));
@@ -874,7 +1084,7 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
-                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, void* stream) {
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, void* stream) {
     if (!rep_genotypes || !rep_fitness || !ws || K <= 0 || D <= 0 || B < 0 || (D & 3)) return QDX_ERR_ARG;
     if (task < QDX_TASK_NONE || task > QDX_TASK_SPHERE) return QDX_ERR_ARG;
     if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
@@ -897,6 +1107,11 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
     p.iso_sigma = iso_sigma; p.line_sigma = line_sigma; p.has_min = has_min; p.has_max = has_max; p.minv = minval; p.maxv = maxval;
     p.out_g = out_genotypes; p.out_f = out_fitness; p.out_d = out_desc; p.out_cell = out_cells; p.out_p1 = out_p1; p.out_p2 = out_p2;
     p.desc_dim = desc_dim; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
+    if (gen_keys8) {
+        p.keys_by_value = 1;
+        p.keys.sel1 = QdxKey{gen_keys8[0], gen_keys8[1]}; p.keys.sel2 = QdxKey{gen_keys8[2], gen_keys8[3]};
+        p.keys.line = QdxKey{gen_keys8[4], gen_keys8[5]}; p.keys.leaf = QdxKey{gen_keys8[6], gen_keys8[7]};
+    }
     const size_t smem = ((size_t)QDX_GEN_WARPS * 32 * p.DS + (size_t)p.grid.total_axes) * sizeof(float);
     const dim3 g((unsigned)((B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32)));
     // arm.py:27 clip(params, 0, 1) is the identity when the variation already clipped into [0, 1]
@@ -986,15 +1201,123 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
     return 0;
 }
 
+static int launch_elect(int32_t task, void* ws, int64_t K, int64_t D, int32_t desc_dim, int64_t B_dev, int32_t nranks,
+                        const float* rep_g, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
+                        float maxval, int32_t first_wins, float* sg, float* sf, float* sd, int32_t wait_peers, cudaStream_t st) {
+    int64_t ctas = (K + 7) / 8;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+#define QDX_ELECT(T) qdx_elect_kernel<T><<<(unsigned)ctas, 256, 0, st>>>(ws, K, (int32_t)D, desc_dim, B_dev, nranks, rep_g, iso_sigma, \
+        line_sigma, has_min, minval, has_max, maxval, first_wins, sg, sf, sd, wait_peers)
+    switch (task) {
+        case QDX_TASK_NONE: QDX_ELECT(QDX_TASK_NONE); break;
+        case QDX_TASK_ARM: QDX_ELECT(QDX_TASK_ARM); break;
+        case QDX_TASK_RASTRIGIN: QDX_ELECT(QDX_TASK_RASTRIGIN); break;
+        default: QDX_ELECT(QDX_TASK_SPHERE); break;
+    }
+#undef QDX_ELECT
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
 int qdx_regenerate_winners(void* ws, int64_t K, int64_t D, int64_t B_dev, int32_t nranks, const float* rep_genotypes,
                            float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
                            int32_t first_wins, float* stage_genotypes, void* stream) {
     if (!ws || !rep_genotypes || !stage_genotypes || K <= 0 || D <= 0 || B_dev <= 0 || nranks < 1 || nranks > QDX_MAX_RANKS) return QDX_ERR_ARG;
-    int64_t ctas = (K + 7) / 8;
-    if (ctas > 148 * 8) ctas = 148 * 8;
-    qdx_regen_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, B_dev, nranks, rep_genotypes, iso_sigma, line_sigma,
-                                                           has_min, minval, has_max, maxval, first_wins, stage_genotypes);
+    return launch_elect(QDX_TASK_NONE, ws, K, D, 1, B_dev, nranks, rep_genotypes, iso_sigma, line_sigma, has_min, minval, has_max,
+                        maxval, first_wins, stage_genotypes, nullptr, nullptr, 0, S(stream));
+}
+
+int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc_dim, int64_t B_dev, int32_t nranks,
+                      const float* rep_genotypes, float iso_sigma, float line_sigma, int32_t has_min, float minval,
+                      int32_t has_max, float maxval, int32_t first_wins, float* stage_genotypes, float* stage_fitness,
+                      float* stage_desc, int32_t wait_peers, void* stream) {
+    if (!ws || !rep_genotypes || !stage_genotypes || !stage_fitness || !stage_desc) return QDX_ERR_ARG;
+    if (K <= 0 || D <= 0 || B_dev <= 0 || nranks < 1 || nranks > QDX_MAX_RANKS) return QDX_ERR_ARG;
+    if (task < QDX_TASK_ARM || task > QDX_TASK_SPHERE || desc_dim < 1 || desc_dim > D || desc_dim > 128) return QDX_ERR_ARG;
+    if (task == QDX_TASK_ARM && (desc_dim != 2 || D > 128)) return QDX_ERR_UNSUPPORTED;
+    return launch_elect(task, ws, K, D, desc_dim, B_dev, nranks, rep_genotypes, iso_sigma, line_sigma, has_min, minval, has_max,
+                        maxval, first_wins, stage_genotypes, stage_fitness, stage_desc, wait_peers, S(stream));
+}
+
+// ---- peer-memory exchange buffers (cudaMalloc + cudaIpc: one process per GPU, one NVLink / NVSwitch domain) ----
+int qdx_xchg_bytes(int64_t K, int64_t* bytes) {
+    if (K <= 0 || K >= (1ll << 31) || !bytes) return QDX_ERR_ARG;
+    *bytes = (int64_t)qdx_xchg_total_bytes(K);
+    return 0;
+}
+
+int qdx_xchg_create(int64_t K, void** buf, void* ipc_handle64) {
+    if (K <= 0 || K >= (1ll << 31) || !buf || !ipc_handle64) return QDX_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, qdx_xchg_total_bytes(K));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, qdx_xchg_total_bytes(K));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle64, p);
+    if (e != cudaSuccess) { cudaFree(p); return (int)e; }
+    *buf = p;
+    return 0;
+}
+
+int qdx_xchg_open(const void* ipc_handle64, void** peer_buf) {
+    if (!ipc_handle64 || !peer_buf) return QDX_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(peer_buf, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int qdx_xchg_close(void* peer_buf) { return peer_buf ? (int)cudaIpcCloseMemHandle(peer_buf) : QDX_ERR_ARG; }
+int qdx_xchg_destroy(void* buf) { return buf ? (int)cudaFree(buf) : QDX_ERR_ARG; }
+
+int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, void* stream) {
+    if (!ws || nranks < 0 || nranks > QDX_MAX_PEERS || (nranks > 0 && (!bufs || rank < 0 || rank >= nranks))) return QDX_ERR_ARG;
+    struct { uint32_t push_ticket, pad0; unsigned long long peer[QDX_MAX_PEERS]; int32_t rank, nranks; } h;
+    static_assert(offsetof(QdxWorkspace, xchg_nranks) - offsetof(QdxWorkspace, push_ticket) + sizeof(int32_t) == sizeof(h), "layout");
+    memset(&h, 0, sizeof(h));
+    for (int q = 0; q < nranks; ++q) { if (!bufs[q]) return QDX_ERR_ARG; h.peer[q] = (unsigned long long)bufs[q]; }
+    h.rank = rank; h.nranks = nranks;
+    return (int)cudaMemcpyAsync((char*)ws + offsetof(QdxWorkspace, push_ticket), &h, sizeof(h), cudaMemcpyHostToDevice, S(stream));
+}
+
+int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream) {
+    if (!ws || K <= 0 || !gen_keys8) return QDX_ERR_ARG;
+    QdxGenKeys g;
+    g.sel1 = QdxKey{gen_keys8[0], gen_keys8[1]}; g.sel2 = QdxKey{gen_keys8[2], gen_keys8[3]};
+    g.line = QdxKey{gen_keys8[4], gen_keys8[5]}; g.leaf = QdxKey{gen_keys8[6], gen_keys8[7]};
+    int64_t ctas = (K + 255) / 256;
+    if (ctas > 148) ctas = 148;
+    qdx_push_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, g);
     QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+// jax.random.split(key, n): out[2 i .. 2 i + 1] = threefry(key, counter = (0, i))
+int qdx_host_split(uint32_t k0, uint32_t k1, int32_t n, uint32_t* out) {
+    if (n < 0 || (n > 0 && !out)) return QDX_ERR_ARG;
+    for (int32_t i = 0; i < n; ++i) h_threefry2x32(k0, k1, 0u, (uint32_t)i, &out[2 * i], &out[2 * i + 1]);
+    return 0;
+}
+
+// Generation keys {sel1, sel2, line, leaf} (2 words each) for the key handed to MAPElites.update (key_mode 1),
+// one scan_update step on carry_io (2; carry_io advanced), DistributedMAPElites.update (3), MixingEmitter.emit (4).
+int qdx_host_generation_keys(int32_t key_mode, uint32_t k0, uint32_t k1, uint32_t* carry_io2, uint32_t* out_keys8) {
+    if (!out_keys8 || key_mode < 1 || key_mode > 4 || (key_mode == 2 && !carry_io2)) return QDX_ERR_ARG;
+    QdxKey key{k0, k1};
+    if (key_mode == 2) {                                                    // map_elites.py:214
+        const QdxKey c{carry_io2[0], carry_io2[1]};
+        key = h_split(c, 1);
+        const QdxKey n = h_split(c, 0);
+        carry_io2[0] = n.a; carry_io2[1] = n.b;
+    }
+    QdxKey emit = key;
+    if (key_mode == 1 || key_mode == 2) emit = h_split(h_split(key, 1), 1);    // map_elites.py:177, :241
+    else if (key_mode == 3) emit = h_split(key, 1);                          // distributed_map_elites.py:124
+    const QdxKey e0 = h_split(emit, 0), e1 = h_split(emit, 1), kv = h_split(emit, 2);   // standard_emitters.py:55
+    const QdxKey sel1 = h_split(e0, 1), sel2 = h_split(e1, 1);               // uniform_selector.py:48
+    const QdxKey line = h_split(kv, 1), leaf = h_split(h_split(kv, 0), 0);   // mutation_operators.py:205, :220
+    const uint32_t w[8] = {sel1.a, sel1.b, sel2.a, sel2.b, line.a, line.b, leaf.a, leaf.b};
+    for (int j = 0; j < 8; ++j) out_keys8[j] = w[j];
     return 0;
 }
 

@@ -90,22 +90,26 @@ QDX_DEV float qdx_log1pf(float y) {
 // XLA ErfInv32 (Giles), fused Horner.  EDGE: handle |x| == 1 (never produced by jax.random.normal's uniform).
 // The tail polynomial (w >= 5, 0.3 % of draws) is entered by a warp-uniform vote so the common path is straight-line.
 // FULLWARP: the caller guarantees all 32 lanes are converged here (saves the activemask query).
-template <bool EDGE, bool FULLWARP>
-QDX_DEV float qdx_erfinvf_t(float x) {
-    float w = -qdx_log1pf(-(x * x));
+QDX_DEV float qdx_erfinv_central_poly(float w) {
+    w = w - 2.5f;
+    float p = 2.81022636e-08f;
+    p = __fmaf_rn(p, w, 3.43273939e-07f);
+    p = __fmaf_rn(p, w, -3.5233877e-06f);
+    p = __fmaf_rn(p, w, -4.39150654e-06f);
+    p = __fmaf_rn(p, w, 0.00021858087f);
+    p = __fmaf_rn(p, w, -0.00125372503f);
+    p = __fmaf_rn(p, w, -0.00417768164f);
+    p = __fmaf_rn(p, w, 0.246640727f);
+    p = __fmaf_rn(p, w, 1.50140941f);
+    return p;
+}
+// p(w) given w = -log1p(-x^2): central polynomial when the whole warp is central, else per-lane coefficients
+template <bool FULLWARP>
+QDX_DEV float qdx_erfinv_poly(float w) {
     float p;
     const bool central = w < 5.0f;
     if (__all_sync(FULLWARP ? 0xffffffffu : __activemask(), central)) {
-        w = w - 2.5f;
-        p = 2.81022636e-08f;
-        p = __fmaf_rn(p, w, 3.43273939e-07f);
-        p = __fmaf_rn(p, w, -3.5233877e-06f);
-        p = __fmaf_rn(p, w, -4.39150654e-06f);
-        p = __fmaf_rn(p, w, 0.00021858087f);
-        p = __fmaf_rn(p, w, -0.00125372503f);
-        p = __fmaf_rn(p, w, -0.00417768164f);
-        p = __fmaf_rn(p, w, 0.246640727f);
-        p = __fmaf_rn(p, w, 1.50140941f);
+        p = qdx_erfinv_central_poly(w);
     } else {
         // mixed warp: both polynomials share one Horner chain with per-lane coefficients
         w = central ? w - 2.5f : __fsqrt_rn(w) - 3.0f;
@@ -119,6 +123,12 @@ QDX_DEV float qdx_erfinvf_t(float x) {
         p = __fmaf_rn(p, w, central ? 0.246640727f : 1.00167406f);
         p = __fmaf_rn(p, w, central ? 1.50140941f : 2.83297682f);
     }
+    return p;
+}
+template <bool EDGE, bool FULLWARP>
+QDX_DEV float qdx_erfinvf_t(float x) {
+    const float w = -qdx_log1pf(-(x * x));
+    const float p = qdx_erfinv_poly<FULLWARP>(w);
     if (EDGE && fabsf(x) == 1.0f) return x * 3.40282347e+38f;
     return p * x;
 }
@@ -133,6 +143,29 @@ QDX_DEV float qdx_normal_from_bits_t(uint32_t bits) {
     return 0x1.6a09e6p+0f * qdx_erfinvf_t<false, FULLWARP>(u);   // u in [lo, 1): |u| == 1 impossible
 }
 QDX_DEV float qdx_normal_from_bits(uint32_t bits) { return qdx_normal_from_bits_t<false>(bits); }
+// Four normals from four draws, all 32 lanes converged: the Threefry blocks that produced `bits`, the uniform -> w
+// transforms and (when all 128 draws of the warp are central, 68 % of the time) the four Horner chains are straight-line
+// code with four independent dependency chains -- the per-draw version is one serial chain with a branch per draw.
+// Same operations per draw, so the results are bit-identical to qdx_normal_from_bits.
+QDX_DEV void qdx_normal4_from_bits(const uint32_t bits[4], float out[4]) {
+    const float lo = -0x1.fffffep-1f;
+    float u[4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float f = qdx_unit_float(bits[j]);
+        float v = f * 2.0f + lo;
+        u[j] = v < lo ? lo : v;
+        w[j] = -qdx_log1pf(-(u[j] * u[j]));
+    }
+    const bool central = (w[0] < 5.0f) & (w[1] < 5.0f) & (w[2] < 5.0f) & (w[3] < 5.0f);
+    if (__all_sync(0xffffffffu, central)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = 0x1.6a09e6p+0f * (qdx_erfinv_central_poly(w[j]) * u[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = 0x1.6a09e6p+0f * (qdx_erfinv_poly<true>(w[j]) * u[j]);
+    }
+}
 // sin & cos: 3-term Cody-Waite by pi/2 (fused), minimax kernels on [-pi/4, pi/4].
 QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
     float q = rintf(th * 0x1.45f306p-1f);

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Sequence, Union
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -47,9 +49,13 @@ def key_data(k) -> np.ndarray:
 
 
 def split(k, num: int = 2) -> np.ndarray:
-    """jax.random.split(key, num) -> (num, 2) uint32; rows unpack like `key, subkey = split(key)`."""
+    """jax.random.split(key, num) -> (num, 2) uint32; rows unpack like `key, subkey = split(key)`.  Host-side
+    (libqdx.so's qdx_host_split; `_threefry2x32` above is the same block in Python, kept for num >= 2^31)."""
     k0, k1 = _native.key_words(k)
     out = np.empty((num, 2), dtype=np.uint32)
+    if num < (1 << 31):
+        _native.call("qdx_host_split", C.c_uint32(k0), C.c_uint32(k1), C.c_int32(num), C.c_void_p(out.ctypes.data))
+        return out
     for i in range(num):
         out[i] = _threefry2x32(k0, k1, (i >> 32) & _M32, i & _M32)
     return out

@@ -60,7 +60,7 @@ def run(task, scoring, cent_t, B_dev, D, iters, exchange):
     # scan() API == the loop above
     return rep
 
-for exchange in ("allgather", "winners", "regen"):
+for exchange in ("allgather", "winners", "regen", "p2p"):
     grid = compute_euclidean_centroids((16, 16), 0.0, 1.0, device=dev)
     run("arm", arm_scoring_function, grid, 300, 20, 4, exchange)
     cvt = torch.from_numpy(np.random.default_rng(0).random((500, 2)).astype(np.float32)).to(dev)

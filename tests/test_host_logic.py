@@ -60,6 +60,33 @@ def test_host_key_chain_matches_oracle():
     assert key.tolist() == [1832780943, 270669613] and sub.tolist() == [64467757, 2916123636]
 
 
+def test_host_generation_keys_follow_the_reference_split_chain():
+    """qdx_host_generation_keys == the jax.random.split chain spelled out in SURVEY.md Appendix B (map_elites.py:177,214,241;
+    distributed_map_elites.py:124; standard_emitters.py:55; uniform_selector.py:48; mutation_operators.py:205,220)."""
+    from qdax_b200 import _native
+
+    def chain(emit):
+        k1, k2, kv = jr.split(emit, 3)
+        kv2, kl = jr.split(kv)
+        return np.concatenate([jr.split(k1)[1], jr.split(k2)[1], kl, jr.split(kv2, 1)[0]]).astype(np.uint32)
+
+    for seed in (0, 42, 123456789):
+        key = jr.key(seed)
+        upd = chain(jr.split(jr.split(key)[1])[1])                      # update: split -> ask: split -> emit
+        assert np.array_equal(np.array(list(_native.host_generation_keys(_native.KEYMODE_UPDATE, key))), upd)
+        dst = chain(jr.split(key)[1])                                   # distributed update: split -> emit
+        assert np.array_equal(np.array(list(_native.host_generation_keys(_native.KEYMODE_DIST_UPDATE, key))), dst)
+        assert np.array_equal(np.array(list(_native.host_generation_keys(_native.KEYMODE_EMIT, key))), chain(key))
+        carry = np.array(key, dtype=np.uint32)                          # scan_update: key, subkey = split(key); update(subkey)
+        ref_carry = np.array(key, dtype=np.uint32)
+        for _ in range(3):
+            got = np.array(list(_native.host_generation_keys(_native.KEYMODE_SCAN, None, carry)))
+            nxt, sub = jr.split(ref_carry)
+            assert np.array_equal(got, chain(jr.split(jr.split(sub)[1])[1]))
+            ref_carry = np.array(nxt, dtype=np.uint32)
+            assert np.array_equal(carry, ref_carry)
+
+
 def test_no_cpu_fallback():
     import torch
 
