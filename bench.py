@@ -7,7 +7,7 @@ fits one GPU, so the same workload is used at every N): arm 100-DoF, grid 100x10
 replicated repertoire, per-rank keys split(key, N)[rank].  A step = ONE full generation: select parents ->
 variation -> arm scoring -> cell assignment -> per-cell best -> [exchange] -> commit into the repertoire -> QD metrics.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--exchange regen|winners|allgather] [--config c1|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--exchange p2p|regen|winners|allgather] [--config c1|c2|c3]
     python bench.py --impl reference ...      # CPU arm: the oracle port of the reference path on the host cores
 
 One JSON line on stdout (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on both
@@ -367,6 +367,7 @@ def run_gpu(args, cfg):
                 "note": "inputs of a step are the 2-word RNG key (host) and the HBM-resident repertoire (carried state)"},
         "gpu_launches": launches, "kernel_ms": kern_ms, "roofline": roofline, "insert_roofline": insert,
         "clocks": clocks, "replicas_bit_identical": consistent,
+        "exchange_used": (getattr(me, "_exchange", "none") if world > 1 else "none"), "exchange_fallback": getattr(me, "exchange_fallback", None),
         "final": {"coverage": coverage, "qd_score": qd, "inserted_last_step": added_last},
     }
     if cpu is not None:
@@ -428,7 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
-    ap.add_argument("--exchange", default="regen", choices=["p2p", "regen", "winners", "allgather"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "regen", "winners", "allgather"])
     ap.add_argument("--cpu-sample", type=int, default=1 << 16, help="offspring per generation in the CPU arm")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

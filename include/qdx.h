@@ -76,12 +76,16 @@ int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t ke
  * out_genotypes may be NULL when the offspring rows are not needed (winners are re-read by qdx_commit, so
  * pass NULL only with offer = 0).
  * gen_keys8: the generation keys {sel1, sel2, line, leaf} derived on the host (qdx_host_generation_keys), or NULL
- * to use the keys qdx_select_prepare left in the workspace. */
+ * to use the keys qdx_select_prepare left in the workspace.
+ * cvt: bucket index over non-grid centroids (qdx_cvt_index below, desc_dim <= 3) or NULL; with it the cell assignment
+ * (and the offer) of a CVT tessellation is fused like the grid fast path. */
+struct qdx_cvt_index;
 int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
-                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, void* stream);
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8,
+                 const struct qdx_cvt_index* cvt, void* stream);
 
 /* ---- stage (b) standalone: arm_scoring_function / rastrigin_scoring_function / sphere_scoring_function */
 int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
@@ -92,6 +96,27 @@ int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_
 int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const qdx_grid_desc* grid,
               int32_t* out_cells, void* ws, const float* rep_fitness, const float* fitness, int32_t offer,
               uint32_t idx_base, int32_t first_wins, void* stream);
+
+/* ---- stage (c) through a uniform bucket index, for low-dimensional CVT tessellations (desc_dim <= 3): same result as
+ * qdx_cells (bit-exact first-index argmin of the reference expression) at ~30 instead of K distance evaluations per
+ * descriptor.  The index is built once per tessellation on the host: qdx_cvt_index_plan fills g / lo / h and the
+ * bucket count (QDX_ERR_UNSUPPORTED: no index applies, use qdx_cells), qdx_cvt_index_build fills start (n_buckets + 1),
+ * ids (K) and pts (K * dd) host arrays, which the caller uploads and points the descriptor at. */
+typedef struct qdx_cvt_index {
+    int32_t dd;           /* 0 = none */
+    int32_t g[3];         /* buckets per dimension; bucket id = b0 + g0 * (b1 + g1 * b2) */
+    float lo[3];          /* lower corner of the centroids' bounding box */
+    float h[3];           /* bucket width */
+    const int32_t* start; /* device */
+    const int32_t* ids;   /* device */
+    const float* pts;     /* device */
+} qdx_cvt_index;
+int qdx_cvt_index_plan(const float* centroids_host, int64_t K, int32_t desc_dim, qdx_cvt_index* plan, int64_t* n_buckets);
+int qdx_cvt_index_build(const float* centroids_host, int64_t K, const qdx_cvt_index* plan, int32_t* start_host, int32_t* ids_host,
+                        float* pts_host);
+int qdx_cells_indexed(const float* desc, int64_t B, const qdx_cvt_index* index, int64_t K, int32_t* out_cells, void* ws,
+                      const float* rep_fitness, const float* fitness, int32_t offer, uint32_t idx_base, int32_t first_wins,
+                      void* stream);
 
 /* ---- stage (c) on the tensor cores, for high-dimensional CVT descriptors (desc_dim <= 32): same result as
  * qdx_cells (bit-exact argmin of the reference expression): tcgen05 TF32 pass -> candidates within a proven error
@@ -141,9 +166,11 @@ int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc
  * Each rank owns an exchange buffer (arrival flags + two key tables, double-buffered by generation parity) created
  * with cudaMalloc and exported with cudaIpc (64-byte handle, exchanged by the host: torch.distributed
  * all_gather_object); qdx_xchg_attach records every rank's mapping in the workspace, after which offers go to the
- * exchange table, qdx_xchg_push max-merges this rank's non-empty entries and its generation keys into every peer
- * (system-scope atomicMax over NVLink) and raises its arrival flag there, and qdx_elect_winners(wait_peers = 1)
- * consumes.  nranks <= 16.  All ranks must call the same sequence of generations (the epoch counter lives on the device).
+ * exchange table AND -- when they improve the cell's local best -- straight into every peer's table (system-scope
+ * atomicMax over NVLink, issued by the offering thread inside qdx_generate / qdx_cells*), the last CTA of a fused
+ * qdx_generate (offer != 0, gen_keys8 given) publishes this rank's generation keys and raises its arrival flag in every
+ * peer (qdx_xchg_push does the same from a 1-thread kernel after un-fused cells kernels), and
+ * qdx_elect_winners(wait_peers = 1) consumes.  nranks <= 16.  All ranks must call the same sequence of generations (the epoch counter lives on the device).
  * qdx_xchg_attach(nranks = 0) detaches. */
 int qdx_xchg_bytes(int64_t K, int64_t* bytes);
 int qdx_xchg_create(int64_t K, void** buf, void* ipc_handle64);

@@ -41,6 +41,18 @@ class GridDesc(C.Structure):
     ]
 
 
+class CvtIndexDesc(C.Structure):
+    _fields_ = [
+        ("dd", C.c_int32),
+        ("g", C.c_int32 * 3),
+        ("lo", C.c_float * 3),
+        ("h", C.c_float * 3),
+        ("start", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("pts", C.c_void_p),
+    ]
+
+
 _i32, _i64, _u32, _f32, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_void_p
 
 # name -> argtypes, exactly the prototypes of include/qdx.h
@@ -54,7 +66,7 @@ PROTOTYPES = {
     "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
     "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],
     "qdx_generate": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _i32,
-                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), _vp],
+                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(CvtIndexDesc), _vp],
     "qdx_elect_winners": [_vp, _i64, _i64, _i32, _i32, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                           _i32, _vp],
     "qdx_xchg_bytes": [_i64, C.POINTER(_i64)],
@@ -68,6 +80,9 @@ PROTOTYPES = {
     "qdx_host_generation_keys": [_i32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)],
     "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],
     "qdx_cells": [_vp, _i64, _i32, _vp, _i64, C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
+    "qdx_cvt_index_plan": [_vp, _i64, _i32, C.POINTER(CvtIndexDesc), C.POINTER(_i64)],
+    "qdx_cvt_index_build": [_vp, _i64, C.POINTER(CvtIndexDesc), _vp, _vp, _vp],
+    "qdx_cells_indexed": [_vp, _i64, C.POINTER(CvtIndexDesc), _i64, _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
     "qdx_cells_tc_workspace": [_i64, _i64, C.POINTER(_i64), C.POINTER(_i64)],
     "qdx_cells_tc_prepare": [_vp, _i64, _i32, _vp, _vp],
     "qdx_cells_tc": [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
@@ -107,7 +122,7 @@ def lib() -> C.CDLL:
 
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
-KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
+KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_indexed": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
                    "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0

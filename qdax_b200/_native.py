@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from qdax_b200 import _lib
-from qdax_b200._lib import GridDesc, call
+from qdax_b200._lib import CvtIndexDesc, GridDesc, call
 
 TASK_IDS = {None: -1, "none": -1, "arm": 0, "rastrigin": 1, "sphere": 2}
 KEYMODE_KEEP, KEYMODE_UPDATE, KEYMODE_SCAN, KEYMODE_DIST_UPDATE, KEYMODE_EMIT = 0, 1, 2, 3, 4
@@ -162,6 +162,63 @@ def grid_of(centroids: torch.Tensor) -> Optional[Grid]:
     return cache[1]
 
 
+# ------------------------------------------------------------------------------------------ CVT bucket index
+@dataclass
+class CvtIndex:
+    """Uniform bucket index over low-dimensional (Dd <= 3) non-grid centroids; built once per tessellation on the host
+    by libqdx.so (qdx_cvt_index_plan / qdx_cvt_index_build) and uploaded.  Keeps the device arrays alive."""
+
+    desc: CvtIndexDesc
+    start: torch.Tensor
+    ids: torch.Tensor
+    pts: torch.Tensor
+
+
+def build_cvt_index(centroids: torch.Tensor) -> Optional[CvtIndex]:
+    c = np.ascontiguousarray(centroids.detach().cpu().numpy(), dtype=np.float32)
+    K, Dd = c.shape
+    plan = CvtIndexDesc()
+    nb = C.c_int64(0)
+    rc = _lib.lib().qdx_cvt_index_plan(C.c_void_p(c.ctypes.data), C.c_int64(K), C.c_int32(Dd), C.byref(plan), C.byref(nb))
+    if rc == -2:                                    # QDX_ERR_UNSUPPORTED: no index applies
+        return None
+    if rc != 0:
+        raise _lib.QdxError("qdx_cvt_index_plan", rc)
+    start = np.empty(nb.value + 1, dtype=np.int32)
+    ids = np.empty(K, dtype=np.int32)
+    pts = np.empty((K, Dd), dtype=np.float32)
+    call("qdx_cvt_index_build", C.c_void_p(c.ctypes.data), C.c_int64(K), C.byref(plan), C.c_void_p(start.ctypes.data),
+         C.c_void_p(ids.ctypes.data), C.c_void_p(pts.ctypes.data))
+    dev = centroids.device
+    ts, ti, tp = torch.from_numpy(start).to(dev), torch.from_numpy(ids).to(dev), torch.from_numpy(pts).to(dev)
+    plan.start, plan.ids, plan.pts = ts.data_ptr(), ti.data_ptr(), tp.data_ptr()
+    return CvtIndex(plan, ts, ti, tp)
+
+
+INDEX_MAX_DIM, INDEX_MIN_CENTROIDS = 3, 256
+
+
+def cvt_index_of(centroids: torch.Tensor) -> Optional[CvtIndex]:
+    """Cached build_cvt_index (cache on the tensor object, keyed on its storage version); None when the tessellation
+    is a grid (fast path), too small, or more than 3-dimensional."""
+    K, Dd = centroids.shape
+    if Dd > INDEX_MAX_DIM or K < INDEX_MIN_CENTROIDS:
+        return None
+    cache = getattr(centroids, "_qdx_index_cache", None)
+    ver = (centroids.data_ptr(), centroids._version, tuple(centroids.shape))
+    if cache is None or cache[0] != ver:
+        cache = (ver, build_cvt_index(centroids))
+        try:
+            centroids._qdx_index_cache = cache
+        except AttributeError:
+            pass
+    return cache[1]
+
+
+def _index_ptr(index: Optional[CvtIndex]):
+    return C.byref(index.desc) if index is not None else C.POINTER(CvtIndexDesc)()
+
+
 def _grid_ptr(grid: Optional[Grid]):
     return C.byref(grid.desc) if grid is not None else C.POINTER(GridDesc)()
 
@@ -193,6 +250,10 @@ def host_generation_keys(key_mode: int, key=None, carry: Optional[np.ndarray] = 
     return out
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """cudaIpc / peer access is not available between the ranks (raised on every rank alike)."""
+
+
 class PeerExchange:
     """Peer-memory exchange buffers of DistributedMAPElites(exchange="p2p"): this rank's buffer (cudaMalloc, exported
     with cudaIpc) and the mappings of every peer's buffer.  torch.distributed is used only to hand the 64-byte IPC
@@ -205,21 +266,36 @@ class PeerExchange:
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
         self.K = K
         self.local = C.c_void_p(0)
-        handle = (C.c_char * 64)()
-        call("qdx_xchg_create", C.c_int64(K), C.byref(self.local), C.cast(handle, C.c_void_p))
-        handles = [None] * self.size
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
         self.peers = (C.c_void_p * self.size)()
         self._opened = []
-        for q in range(self.size):
-            if q == self.rank:
-                self.peers[q] = self.local.value
-            else:
-                pp = C.c_void_p(0)
-                hb = C.create_string_buffer(handles[q], 64)
-                call("qdx_xchg_open", C.cast(hb, C.c_void_p), C.byref(pp))
-                self.peers[q] = pp.value
-                self._opened.append(pp.value)
+        handle = (C.c_char * 64)()
+        err: Optional[Exception] = None
+        try:
+            call("qdx_xchg_create", C.c_int64(K), C.byref(self.local), C.cast(handle, C.c_void_p))
+        except _lib.QdxError as e:
+            err = e
+        handles = [None] * self.size
+        dist.all_gather_object(handles, None if err is not None else bytes(handle.raw), group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for q in range(self.size):
+                    if q == self.rank:
+                        self.peers[q] = self.local.value
+                    else:
+                        pp = C.c_void_p(0)
+                        hb = C.create_string_buffer(handles[q], 64)
+                        call("qdx_xchg_open", C.cast(hb, C.c_void_p), C.byref(pp))
+                        self.peers[q] = pp.value
+                        self._opened.append(pp.value)
+            except _lib.QdxError as e:
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not create its exchange buffer")
+        oks = [None] * self.size                    # every rank must take the same decision
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            self.close()
+            raise PeerExchangeUnavailable(str(err) if err is not None else "a peer could not map the exchange buffers")
         torch.cuda.synchronize()
         dist.barrier(group=group)          # every rank's buffer is zeroed and mapped before anybody pushes
 
@@ -231,10 +307,11 @@ class PeerExchange:
             ws.xchg = self
 
     def close(self) -> None:
+        torch.cuda.synchronize()
+        for p in self._opened:
+            call("qdx_xchg_close", C.c_void_p(p))
+        self._opened = []
         if self.local.value:
-            torch.cuda.synchronize()
-            for p in self._opened:
-                call("qdx_xchg_close", C.c_void_p(p))
             call("qdx_xchg_destroy", self.local)
             self.local = C.c_void_p(0)
 
@@ -262,13 +339,13 @@ def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: i
 
 def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, line_sigma: float, minval, maxval,
              task: Optional[str], desc_dim: int, grid: Optional[Grid], offer: bool, idx_base: int, first_wins: bool,
-             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None, gen_keys=None) -> None:
+             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None, gen_keys=None, index: Optional[CvtIndex] = None) -> None:
     K, D = rep_g.shape
     call("qdx_generate", _ptr(rep_g), _ptr(rep_f), _ptr(centroids), ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B),
          C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
          C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim),
          _grid_ptr(grid), C.c_int32(bool(offer)), C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _ptr(out_g), _ptr(out_f),
-         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _stream())
+         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _index_ptr(index), _stream())
 
 
 def score(task: str, g: torch.Tensor, desc_dim: int = 2, out_f: Optional[torch.Tensor] = None,
@@ -319,12 +396,19 @@ def cells_tc(desc: torch.Tensor, centroids: torch.Tensor, ws: Optional["Workspac
 
 def cells(desc: torch.Tensor, centroids: torch.Tensor, grid: Optional[Grid] = None, ws: Optional[Workspace] = None,
           rep_f: Optional[torch.Tensor] = None, fitness: Optional[torch.Tensor] = None, offer: bool = False,
-          idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None, allow_tc: bool = True) -> torch.Tensor:
+          idx_base: int = 0, first_wins: bool = True, out: Optional[torch.Tensor] = None, allow_tc: bool = True,
+          allow_index: bool = True) -> torch.Tensor:
     B, Dd = desc.shape
     if grid is None and allow_tc and TC_MIN_DIM <= Dd <= TC_MAX_DIM and centroids.shape[0] >= TC_MIN_CENTROIDS and B > 0:
         return cells_tc(desc, centroids, ws, rep_f, fitness, offer, idx_base, first_wins, out)
     if out is None:
         out = torch.empty(B, dtype=torch.int32, device=desc.device)
+    index = cvt_index_of(centroids) if (grid is None and allow_index and B > 0) else None
+    if index is not None:
+        call("qdx_cells_indexed", _ptr(desc), C.c_int64(B), _index_ptr(index), C.c_int64(centroids.shape[0]), _ptr(out),
+             C.c_void_p(0) if ws is None else ws.ptr, _ptr(rep_f), _ptr(fitness), C.c_int32(bool(offer)), C.c_uint32(idx_base),
+             C.c_int32(bool(first_wins)), _stream())
+        return out
     call("qdx_cells", _ptr(desc), C.c_int64(B), C.c_int32(Dd), _ptr(centroids), C.c_int64(centroids.shape[0]), _grid_ptr(grid),
          _ptr(out), C.c_void_p(0) if ws is None else ws.ptr, _ptr(rep_f), _ptr(fitness), C.c_int32(bool(offer)),
          C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _stream())

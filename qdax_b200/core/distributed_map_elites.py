@@ -12,11 +12,13 @@ rank * B_dev + i), same per-rank key chain (`key, subkey = split(key)`; emit(sub
                         rank's generation keys in tail slots; every rank then REGENERATES the winners from (owner's
                         keys, local index) -- the RNG is counter-based and the repertoire replicated -- scores them
                         and commits.  No genotype crosses NVLink.
-  exchange="p2p"        the regen exchange without a collective library: every rank max-merges its non-empty key-table
-                        entries and its generation keys straight into every peer's table with system-scope 64-bit
-                        atomicMax over NVLink (buffers mapped with cudaIpc, double-buffered by generation parity) and
-                        raises an arrival flag there; the elect kernel acquire-spins on its local flags, then
-                        regenerates + scores the winners.  generate -> push -> elect -> commit, no host involvement.
+  exchange="p2p"        the regen exchange without a collective library, fused into the compute: an offer that improves
+                        its cell's local best is max-merged by the offering thread straight into every peer's key table
+                        (system-scope 64-bit atomicMax over NVLink; buffers mapped with cudaIpc, double-buffered by
+                        generation parity); the last CTA of the generate kernel publishes the rank's generation keys
+                        and raises an arrival flag in every peer; the elect kernel acquire-spins on its local flags,
+                        then regenerates + scores the winners.  generate -> elect -> commit: three launches, no host
+                        involvement, no collective.
   exchange="winners"    only what can change the repertoire travels: each rank offers its shard into its local
                         64-bit key table, one all-reduce(max) of the K keys elects the global per-cell winners
                         (the global best of a cell is always a local best), winners' rows are merged through a
@@ -48,6 +50,7 @@ class DistributedMAPElites(MAPElites):
         self._group = group
         self._dist_buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._xchg: Optional[_native.PeerExchange] = None
+        self.exchange_fallback: Optional[str] = None
 
     # ------------------------------------------------------------------------------------------ reference API
     def init(self, genotypes, centroids, key) -> Tuple[MapElitesRepertoire, Optional[EmitterState], Dict]:
@@ -94,8 +97,13 @@ class DistributedMAPElites(MAPElites):
         base = rank * B
         if p2p:
             if self._xchg is None or self._xchg.K != K:
-                self._xchg = _native.PeerExchange(K, self._group)
-            self._xchg.attach(ws)
+                try:
+                    self._xchg = _native.PeerExchange(K, self._group)
+                except _native.PeerExchangeUnavailable as e:     # same decision on every rank: NCCL carries the keys instead
+                    self.exchange_fallback = f"p2p unavailable ({e}); using regen"
+                    self._exchange, p2p = "regen", False
+            if p2p:
+                self._xchg.attach(ws)
         gen_keys = _native.host_generation_keys(key_mode, key)
         self._mark("begin")
         if self._exchange == "regen" and R > 1:
@@ -105,10 +113,12 @@ class DistributedMAPElites(MAPElites):
         else:
             _native.ensure_selection(rep_f, ws)
         self._mark("prepare")
+        index = None if grid is not None else _native.cvt_index_of(rep.centroids)
+        fused_cells = grid is not None or index is not None
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
-                         cfg["maxval"], cfg["task"], Dd, grid, winners and grid is not None, base, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys)
-        if grid is None:   # cell assignment stays sharded: each rank assigns only its own offspring
+                         cfg["maxval"], cfg["task"], Dd, grid, winners and fused_cells, base, first,
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index)
+        if not fused_cells:   # cell assignment stays sharded: each rank assigns only its own offspring
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=winners, idx_base=base, first_wins=first, out=buf["c"])
         self._mark("generate")
         if not winners:
@@ -131,7 +141,10 @@ class DistributedMAPElites(MAPElites):
         sg, sd, sf = _stage_views(st, D, Dd)
         if self._exchange in ("regen", "p2p"):
             if p2p:
-                _native.xchg_push(ws, gen_keys)
+                # the offers already pushed their records into every peer (qdx_offer); with fused cell assignment the
+                # last CTA of the generate kernel also published keys + arrival flags, otherwise a 1-thread kernel does
+                if not fused_cells:
+                    _native.xchg_push(ws, gen_keys)
             else:
                 parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
             self._mark("exchange_keys")

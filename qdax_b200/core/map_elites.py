@@ -119,11 +119,13 @@ class MAPElites:
         self._mark("begin")
         _native.ensure_selection(rep_f, ws)
         self._mark("prepare")
+        index = None if grid is not None else _native.cvt_index_of(rep.centroids)   # low-dimensional CVT: bucket index
+        fused_cells = grid is not None or index is not None
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
-                         cfg["maxval"], cfg["task"], cfg["desc_dim"], grid, grid is not None, 0, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys)
+                         cfg["maxval"], cfg["task"], cfg["desc_dim"], grid, fused_cells, 0, first,
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index)
         self._mark("generate")
-        if grid is None:
+        if not fused_cells:
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=True, first_wins=first, out=buf["c"])
             self._mark("cells")
         _native.commit(ws, buf["g"], buf["f"], buf["d"], rep.genotypes, rep_f, rep.descriptors, first_wins=first,

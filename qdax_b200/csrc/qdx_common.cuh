@@ -23,6 +23,9 @@ struct QdxGenKeys {
 };
 
 #define QDX_MAX_COMMIT_CTAS (148 * 8)
+#ifndef QDX_COMMIT_CTAS
+#define QDX_COMMIT_CTAS (148 * 8)      // grid cap of the commit kernel: measured better than one resident wave (148 * 4) for 4 KB rows (0.56 vs 0.42 of HBM peak)
+#endif
 #define QDX_MAX_PEERS 16      // ranks of one NVLink domain whose key tables are mapped into each other (cudaIpc)
 
 // Device workspace header (one per repertoire); arrays follow at fixed offsets (qdx_ws_* below).
@@ -107,13 +110,68 @@ QDX_DEV uint32_t qdx_key_index(unsigned long long key, int first_wins) {
 // Offer offspring `idx` with fitness f to cell c (MapElitesRepertoire.add, mapelites_repertoire.py:211-231):
 // only candidates that can change the outcome touch the table (NaN poisons its cell; f <= current never wins
 // and never blocks a winner because any winner has f > current >= f).
-// With the peer-memory exchange attached, peers push into the same table with system-scope atomics while this rank
-// may still be offering, so the local atomics are system scope too (same L2 operation on local memory).
-QDX_DEV void qdx_offer(void* ws, int64_t K, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
+// With the peer-memory exchange attached (multi-GPU), an offer that becomes its cell's best so far on THIS rank is
+// max-merged straight into every peer's table as well: system-scope 64-bit atomicMax into the peer's HBM over NVLink,
+// issued from inside the generate / cells kernels, so the exchange overlaps the compute and needs no pass of its own.
+// The global best of a cell is some rank's final local best, and a rank's final local best is always an improving
+// record, so every table ends up holding the global maximum.  (~ln(offers per cell) records per cell at cold start,
+// about one per changed cell in steady state.)  The fence makes the remote atomics visible before this thread's warp
+// reports done (qdx_xchg_warp_done).
+QDX_DEV void qdx_offer(void* ws_raw, int64_t K, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
     const float cur = __ldg(rep_f + c);
     if ((f != f) || f > cur) {
-        unsigned long long* slot = qdx_ws_keytab(ws, K) + c;
+        const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
         const unsigned long long key = qdx_pack_key(f, idx, first_wins);
-        if (((const QdxWorkspace*)ws)->xchg_nranks > 0) atomicMax_system(slot, key); else atomicMax(slot, key);
+        const int R = ws->xchg_nranks;
+        if (R > 0) {
+            const int me = ws->xchg_rank;
+            const size_t off = qdx_xchg_tab_offset(K, (int)(*(const uint32_t*)((const char*)ws->xchg_peer[me] + QDX_XCHG_EPOCH_OFFSET) & 1u));
+            const unsigned long long old = atomicMax_system((unsigned long long*)((char*)ws->xchg_peer[me] + off) + c, key);
+            if (key > old) {
+                for (int q = 0; q < R; ++q)
+                    if (q != me) atomicMax_system((unsigned long long*)((char*)ws->xchg_peer[q] + off) + c, key);
+                __threadfence_system();
+            }
+        } else {
+            atomicMax((unsigned long long*)((char*)ws_raw + qdx_ws_keytab_offset(K)) + c, key);
+        }
+    }
+}
+
+QDX_DEV void qdx_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+QDX_DEV unsigned long long qdx_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Publication of "rank `me`, epoch e: all my keys have landed": this rank's generation keys go to slot `me` of every
+// rank's table (the winners are REGENERATED by every rank from (owner's keys, local index), so no genotype crosses
+// NVLink), then the arrival flag is raised in every peer (release, system scope).  One thread.
+QDX_DEV void qdx_xchg_publish(QdxWorkspace* ws, int64_t K, const QdxGenKeys& keys) {
+    const int R = ws->xchg_nranks, me = ws->xchg_rank;
+    const uint32_t epoch = *(const uint32_t*)((const char*)ws->xchg_peer[me] + QDX_XCHG_EPOCH_OFFSET);
+    const size_t off = qdx_xchg_tab_offset(K, (int)(epoch & 1u));
+    const uint32_t w[8] = {keys.sel1.a, keys.sel1.b, keys.sel2.a, keys.sel2.b, keys.line.a, keys.line.b, keys.leaf.a, keys.leaf.b};
+    __threadfence_system();
+    for (int q = 0; q < R; ++q) {
+        unsigned long long* slot = (unsigned long long*)((char*)ws->xchg_peer[q] + off) + K + 8 * me;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slot[j] = (unsigned long long)w[j];
+    }
+    __threadfence_system();
+    for (int q = 0; q < R; ++q) qdx_st_release_sys((unsigned long long*)ws->xchg_peer[q] + me, (unsigned long long)(epoch + 1u));
+}
+// Called by one thread of every CTA of an offering kernel when the CTA is done (after __syncthreads; every thread that
+// pushed a record has already fenced at system scope): the last CTA of the grid publishes.
+QDX_DEV void qdx_xchg_cta_done(void* ws_raw, int64_t K, const QdxGenKeys& keys, unsigned total_ctas) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    if (ws->xchg_nranks <= 0) return;
+    __threadfence();
+    if (atomicAdd(&ws->push_ticket, 1u) == total_ctas - 1u) {
+        ws->push_ticket = 0u;
+        qdx_xchg_publish(ws, K, keys);
     }
 }

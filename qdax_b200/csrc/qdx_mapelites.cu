@@ -18,7 +18,10 @@
 // qdax/tasks/standard_functions.py:9-48, qdax/core/containers/mapelites_repertoire.py:111-266,
 // qdax/utils/metrics.py:74-98.
 #include "qdx_common.cuh"
+#include "qdx_cells_index.cuh"
 #include "../../include/qdx.h"
+
+int qdx_fill_cvt_index(const qdx_cvt_index* in, QdxCvtIndex* out);     // qdx_cells_index.cu
 
 #define QDX_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
@@ -199,6 +202,7 @@ struct QdxGenParams {
     QdxGrid grid;
     int32_t offer; uint32_t idx_base; int32_t first_wins;
     int32_t keys_by_value; QdxGenKeys keys;          // generation keys derived on the host (qdx_host_generation_keys)
+    QdxCvtIndex cvt;                                  // bucket index over non-grid centroids (GRID_DD < 0)
 };
 
 QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
@@ -211,7 +215,21 @@ constexpr int QDX_GEN_WARPS = 4;
 // ARM_CLIP: arm.py:27 clips the genotype to [0,1] before scoring; when the variation already clipped to a range
 // inside [0,1] that clip is the identity and is compiled out (bit-identical result).
 template <int TASK, int GRID_DD, bool ARM_CLIP>
+__device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p);
+
+template <int TASK, int GRID_DD, bool ARM_CLIP>
 __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(const QdxGenParams p) {
+    qdx_generate_body<TASK, GRID_DD, ARM_CLIP>(p);
+    // multi-GPU peer-memory exchange: this CTA's offers (and their pushes into the peers) are done; the last CTA of
+    // the grid publishes this rank's generation keys and raises its arrival flag in every peer
+    if (GRID_DD != 0 && p.offer && p.keys_by_value) {
+        __syncthreads();
+        if (threadIdx.x == 0) qdx_xchg_cta_done(p.ws, p.K, p.keys, gridDim.x);
+    }
+}
+
+template <int TASK, int GRID_DD, bool ARM_CLIP>
+__device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
     extern __shared__ __align__(128) float s_tiles[];
     __shared__ QdxSeg s_seg[QDX_MAX_SEG];
     __shared__ float s_last[QDX_MAX_SEG];
@@ -351,9 +369,10 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
                 const float dy = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
                 p.out_f[row] = fit;
                 reinterpret_cast<float2*>(p.out_d)[row] = make_float2(dx, dy);
-                if (GRID_DD > 0) {
+                if (GRID_DD != 0) {
                     float xd[QDX_MAX_GRID_DIM] = {dx, dy, 0.0f, 0.0f};
-                    const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
+                    const int32_t cell = GRID_DD > 0 ? qdx_grid_cell<(GRID_DD > 0 ? GRID_DD : 1)>(xd, p.grid, s_axes, p.centroids, p.K)
+                                                     : qdx_index_cell<(GRID_DD < 0 ? -GRID_DD : 1)>(xd, p.cvt);
                     if (p.out_cell) p.out_cell[row] = cell;
                     if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
                 }
@@ -383,11 +402,12 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
                     if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
                     const float fit = -f;
                     p.out_f[row] = fit;
-                    if (GRID_DD > 0) {
+                    if (GRID_DD != 0) {
                         float xd[QDX_MAX_GRID_DIM];
 #pragma unroll
-                        for (int j = 0; j < (GRID_DD == 0 ? 1 : GRID_DD); ++j) xd[j] = p.out_d[row * p.desc_dim + j];
-                        const int32_t cell = qdx_grid_cell<GRID_DD == 0 ? 1 : GRID_DD>(xd, p.grid, s_axes, p.centroids, p.K);
+                        for (int j = 0; j < (GRID_DD > 0 ? GRID_DD : -GRID_DD); ++j) xd[j] = p.out_d[row * p.desc_dim + j];
+                        const int32_t cell = GRID_DD > 0 ? qdx_grid_cell<(GRID_DD > 0 ? GRID_DD : 1)>(xd, p.grid, s_axes, p.centroids, p.K)
+                                                         : qdx_index_cell<(GRID_DD < 0 ? -GRID_DD : 1)>(xd, p.cvt);
                         if (p.out_cell) p.out_cell[row] = cell;
                         if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
                     }
@@ -712,58 +732,24 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     __shared__ int32_t s_scan[33];
     int total_new = 0, total_cnt = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) { total_new += s_new[w]; total_cnt += s_cnt[w]; }
+#ifndef QDX_COMMIT_NO_TAIL     // A/B switch for timing only (selection tables would go stale)
     if (total_new != 0 || total_cnt != ws->sel.M || ws->sel.nseg <= 0) qdx_cta_occupancy_scan(rep_f, K, ws_raw, s_scan);
+#endif
 }
 
 // =====================================================================================================
 // peer-memory exchange (multi-GPU): push the local per-cell bests into every peer's key table over NVLink
 // =====================================================================================================
 // DistributedMAPElites (distributed_map_elites.py:133-146) needs, per cell, the best offspring over ALL ranks.  Every
-// rank has already reduced its shard into its own key table (atomicMax offers of the generate / cells kernels); the
-// global best of a cell is always some rank's local best, so it is enough to max-merge the (few) non-empty entries
-// into every peer: system-scope 64-bit atomicMax straight into the peer's HBM (mapped with cudaIpc, NVLink 5 /
-// NVSwitch), no staging, no collective library.  The last CTA then publishes "rank `me`, epoch e has landed" in every
-// peer's flag array (release, system scope); consumers acquire-spin on their LOCAL flags (qdx_elect_kernel).
-QDX_DEV void qdx_st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-QDX_DEV unsigned long long qdx_ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(256) qdx_push_kernel(void* ws_raw, int64_t K, const QdxGenKeys keys) {
-    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
-    const int R = ws->xchg_nranks, me = ws->xchg_rank;
-    const uint32_t epoch = *(const uint32_t*)((const char*)ws->xchg_peer[me] + QDX_XCHG_EPOCH_OFFSET);
-    const size_t tab_off = qdx_xchg_tab_offset(K, (int)(epoch & 1u));
-    __shared__ unsigned long long* s_tab[QDX_MAX_PEERS];
-    __shared__ bool s_last;
-    if (threadIdx.x < R) s_tab[threadIdx.x] = (unsigned long long*)((char*)ws->xchg_peer[threadIdx.x] + tab_off);
-    __syncthreads();
-    // this rank's generation keys -> slot `me` of every rank's table (disjoint slots, plain stores): the winners are
-    // REGENERATED by every rank from (owner's keys, local index), so no genotype crosses NVLink
-    if (blockIdx.x == 0 && threadIdx.x < 8 * R) {
-        const int q = threadIdx.x >> 3, j = threadIdx.x & 7;
-        const uint32_t w[8] = {keys.sel1.a, keys.sel1.b, keys.sel2.a, keys.sel2.b, keys.line.a, keys.line.b, keys.leaf.a, keys.leaf.b};
-        s_tab[q][K + 8 * me + j] = (unsigned long long)w[j];
-    }
-    const unsigned long long* local = s_tab[me];
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < K; c += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long key = __ldcg(local + c);
-        if (key != 0ull)
-            for (int q = 0; q < R; ++q) if (q != me) atomicMax_system(s_tab[q] + c, key);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&ws->push_ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence_system();
-    if (threadIdx.x < R)
-        qdx_st_release_sys((unsigned long long*)ws->xchg_peer[threadIdx.x] + me, (unsigned long long)(epoch + 1u));
-    if (threadIdx.x == 0) ws->push_ticket = 0u;
+// offer that improves its cell's local best is max-merged into every peer's key table by the offering thread itself
+// (qdx_offer: system-scope 64-bit atomicMax straight into the peer's HBM, mapped with cudaIpc, NVLink 5 / NVSwitch; no
+// staging, no collective library).  When the last offering warp of a rank is done it publishes "rank `me`, epoch e has
+// landed" in every peer's flag array (release, system scope; qdx_xchg_warp_done in the generate kernel, or the
+// stand-alone kernel below); consumers acquire-spin on their LOCAL flags (qdx_elect_kernel).
+// Stand-alone publication for generations whose offers come from a separate cells kernel (non-fused tessellations):
+// stream order guarantees every offering kernel (and the system-scope fences of its pushes) has completed.
+__global__ void qdx_publish_kernel(void* ws_raw, int64_t K, const QdxGenKeys keys) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) qdx_xchg_publish((QdxWorkspace*)ws_raw, K, keys);
 }
 
 // =====================================================================================================
@@ -805,11 +791,33 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
     const float total = ws->sel.total;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* s_x = s_buf[wid][0]; float* s_a = s_buf[wid][1]; float* s_b = s_buf[wid][2];
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t c = warp_global; c < K; c += nwarps) {
-        const unsigned long long key = __ldcg(keytab + c);
-        if (key == 0ull || qdx_key_is_nan(key)) continue;
+    // The CTA owns a contiguous block of cells (the grid is one wave): coalesced key loads, the elected cells of
+    // each 256-cell slab are compacted into a shared list, and the 8 warps take them round-robin -- with ~10 % of the
+    // cells elected, every warp gets real work instead of one warp per (mostly empty) cell.
+    __shared__ int32_t s_list[256];
+    __shared__ unsigned long long s_key[256];
+    __shared__ int32_t s_n;
+    const int64_t per_cta = ((K + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;
+    const int64_t c_lo = (int64_t)blockIdx.x * per_cta, c_hi = c_lo + per_cta < K ? c_lo + per_cta : K;
+    for (int64_t slab = c_lo; slab < c_hi; slab += 256) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        {
+            const int64_t c = slab + threadIdx.x;
+            const unsigned long long k = c < c_hi ? __ldcg(keytab + c) : 0ull;
+            const bool el = k != 0ull && !qdx_key_is_nan(k);
+            const unsigned b = __ballot_sync(0xffffffffu, el);
+            int base = 0;
+            if (lane == 0 && b) base = atomicAdd(&s_n, __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (el) { const int pos = base + __popc(b & ((1u << lane) - 1u)); s_list[pos] = (int32_t)(c - slab); s_key[pos] = k; }
+        }
+        __syncthreads();
+        const int n_el = s_n;
+    for (int e = wid; e < n_el; e += 8) {
+        const int64_t c = slab + s_list[e];
+        const unsigned long long key = s_key[e];
         const uint32_t idx = qdx_key_index(key, first_wins);
         const int64_t r = idx / B_dev, i = idx % B_dev;
         if (r >= nranks) continue;
@@ -878,6 +886,7 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
             if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
             stage_f[c] = -f;
         }
+    }
     }
 }
 
@@ -1017,14 +1026,28 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, c
         if (e != cudaSuccess) return (int)e;                                                                       \
         qdx_generate_kernel<TASK, GD, ARM_CLIP><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);                        \
     } while (0)
-    const int gd = (TASK == QDX_TASK_NONE) ? 0 : p.grid.dd;
-    switch (gd) {
-        case 0: QDX_LAUNCH_GEN(0); break;
-        case 1: QDX_LAUNCH_GEN(1); break;
-        case 2: QDX_LAUNCH_GEN(2); break;
-        case 3: QDX_LAUNCH_GEN(3); break;
-        case 4: QDX_LAUNCH_GEN(4); break;
-        default: return QDX_ERR_ARG;
+    const int gd = (TASK == QDX_TASK_NONE) ? 0 : (p.grid.dd ? p.grid.dd : -p.cvt.dd);
+    if (TASK == QDX_TASK_ARM) {            // arm descriptors are 2-D: grid 2, bucket index 2, or none
+        switch (gd) {
+            case 0: QDX_LAUNCH_GEN(0); break;
+            case 2: QDX_LAUNCH_GEN(2); break;
+            case -2: QDX_LAUNCH_GEN(-2); break;
+            default: return QDX_ERR_ARG;
+        }
+    } else if (TASK == QDX_TASK_NONE) {
+        QDX_LAUNCH_GEN(0);
+    } else {
+        switch (gd) {
+            case 0: QDX_LAUNCH_GEN(0); break;
+            case 1: QDX_LAUNCH_GEN(1); break;
+            case 2: QDX_LAUNCH_GEN(2); break;
+            case 3: QDX_LAUNCH_GEN(3); break;
+            case 4: QDX_LAUNCH_GEN(4); break;
+            case -1: QDX_LAUNCH_GEN(-1); break;
+            case -2: QDX_LAUNCH_GEN(-2); break;
+            case -3: QDX_LAUNCH_GEN(-3); break;
+            default: return QDX_ERR_ARG;
+        }
     }
 #undef QDX_LAUNCH_GEN
     QDX_CHECK_LAUNCH();
@@ -1084,7 +1107,8 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
-                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, void* stream) {
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, const qdx_cvt_index* cvt,
+                 void* stream) {
     if (!rep_genotypes || !rep_fitness || !ws || K <= 0 || D <= 0 || B < 0 || (D & 3)) return QDX_ERR_ARG;
     if (task < QDX_TASK_NONE || task > QDX_TASK_SPHERE) return QDX_ERR_ARG;
     if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
@@ -1096,7 +1120,10 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
     memset(&p, 0, sizeof(p));
     int rc = fill_grid(task == QDX_TASK_NONE ? nullptr : grid, desc_dim, &p.grid);
     if (rc) return rc;
-    if (offer && p.grid.dd == 0) return QDX_ERR_ARG;          // offer needs cells: grid fast path only
+    rc = qdx_fill_cvt_index((task == QDX_TASK_NONE || p.grid.dd) ? nullptr : cvt, &p.cvt);
+    if (rc) return rc;
+    if (p.cvt.dd && p.cvt.dd != desc_dim) return QDX_ERR_ARG;
+    if (offer && p.grid.dd == 0 && p.cvt.dd == 0) return QDX_ERR_ARG;   // offer needs cells: grid fast path or bucket index
     if (p.grid.dd && !centroids) return QDX_ERR_ARG;
     p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.centroids = centroids; p.ws = ws;
     p.B = B; p.K = K; p.D = (int32_t)D;
@@ -1191,8 +1218,8 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
                int32_t mode, void* stream) {
     if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
     if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
-    int64_t ctas = (K + 7) / 8;                 // one warp per cell, 8 warps per CTA, grid-stride beyond 148 * 8 CTAs
-    if (ctas > QDX_MAX_COMMIT_CTAS) ctas = QDX_MAX_COMMIT_CTAS;
+    int64_t ctas = (K + 7) / 8;                 // one warp per cell, 8 warps per CTA, grid-stride beyond one wave
+    if (ctas > QDX_COMMIT_CTAS) ctas = QDX_COMMIT_CTAS;
     if (ctas < 1) ctas = 1;
     qdx_commit_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
                                                             idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
@@ -1204,8 +1231,8 @@ int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* of
 static int launch_elect(int32_t task, void* ws, int64_t K, int64_t D, int32_t desc_dim, int64_t B_dev, int32_t nranks,
                         const float* rep_g, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                         float maxval, int32_t first_wins, float* sg, float* sf, float* sd, int32_t wait_peers, cudaStream_t st) {
-    int64_t ctas = (K + 7) / 8;
-    if (ctas > 148 * 8) ctas = 148 * 8;
+    int64_t ctas = (K + 63) / 64;               // >= 64 cells per CTA, at most one wave (3 CTAs of 256 threads per SM)
+    if (ctas > 148 * 3) ctas = 148 * 3;
 #define QDX_ELECT(T) qdx_elect_kernel<T><<<(unsigned)ctas, 256, 0, st>>>(ws, K, (int32_t)D, desc_dim, B_dev, nranks, rep_g, iso_sigma, \
         line_sigma, has_min, minval, has_max, maxval, first_wins, sg, sf, sd, wait_peers)
     switch (task) {
@@ -1285,9 +1312,7 @@ int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream) 
     QdxGenKeys g;
     g.sel1 = QdxKey{gen_keys8[0], gen_keys8[1]}; g.sel2 = QdxKey{gen_keys8[2], gen_keys8[3]};
     g.line = QdxKey{gen_keys8[4], gen_keys8[5]}; g.leaf = QdxKey{gen_keys8[6], gen_keys8[7]};
-    int64_t ctas = (K + 255) / 256;
-    if (ctas > 148) ctas = 148;
-    qdx_push_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, g);
+    qdx_publish_kernel<<<1, 32, 0, S(stream)>>>(ws, K, g);
     QDX_CHECK_LAUNCH();
     return 0;
 }

@@ -72,7 +72,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_distributed_map_elites_nccl(tmp_path, world):
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} CUDA devices")
@@ -80,6 +80,6 @@ def test_distributed_map_elites_nccl(tmp_path, world):
     script.write_text(WORKER)
     env = dict(os.environ, QDX_ROOT=ROOT)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", str(script)]
+           "--master-port", str(29517 + world), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DISTRIBUTED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -263,6 +263,49 @@ def test_cells_bruteforce_cvt(dev, co, K, Dd, B):
     assert np.array_equal(got[:4096], qn.get_cells_indices(desc[:4096], cent))
 
 
+@pytest.mark.parametrize("K,Dd,B,scale,shift", [(10000, 2, 30000, 1.0, 0.0), (1000, 3, 8000, 1.0, 0.0), (300, 1, 2000, 1.0, 0.0),
+                                                (4096, 2, 8000, 1e-3, 5.0), (20000, 3, 8000, 40.0, -20.0), (2000, 2, 4000, 1.0, 0.0)])
+def test_cells_bucket_index_equals_bruteforce(dev, co, K, Dd, B, scale, shift):
+    """Uniform bucket index (Dd <= 3 CVT tessellations) == brute-force first-index argmin, bit for bit: random points inside
+    and outside the bounding box, exact centroid hits and duplicates (ties -> first index), midpoints of centroid pairs,
+    bucket corners / edges +- 1 ulp, clustered centroids, degenerate (anisotropic) boxes, huge and non-finite values."""
+    from qdax_b200 import _native
+
+    rng = np.random.default_rng(K * 7 + Dd)
+    cent = (rng.random((K, Dd)) * scale + shift).astype(np.float32)
+    if K == 2000:
+        cent[:, 1] = cent[:, 1] * np.float32(1e-3)                    # anisotropic box
+    cent[K // 3] = cent[K // 5]                                       # duplicated centroid: first index must win
+    cent[50:90] = cent[49] + (rng.random((40, Dd)) * 1e-5 * scale).astype(np.float32)   # tight cluster in one bucket
+    cent_t = T(cent, dev)
+    index = _native.cvt_index_of(cent_t)
+    if scale < 1e-2:            # box far from the origin and tiny: bucket width below the rounding margins -> no index
+        assert index is None
+        desc = ((rng.random((B, Dd)) * 1.6 - 0.3) * scale + shift).astype(np.float32)
+        assert np.array_equal(N(_native.cells(T(desc, dev), cent_t, None)), co.cells(desc, cent))
+        return
+    assert index is not None and index.desc.dd == Dd
+    lo, hi = cent.min(0), cent.max(0)
+    span = (hi - lo).astype(np.float32)
+    pts = [(rng.random((B, Dd)) * 1.6 - 0.3).astype(np.float32) * span + lo]                      # inside and around the box
+    pts.append(cent[rng.integers(0, K, 512)])                                                     # exact hits
+    pts.append(((cent[rng.integers(0, K, 512)].astype(np.float64) + cent[rng.integers(0, K, 512)]) / 2).astype(np.float32))
+    g = np.array(list(index.desc.g)[:Dd]); h = np.array(list(index.desc.h)[:Dd], np.float32); l0 = np.array(list(index.desc.lo)[:Dd], np.float32)
+    corners = (l0 + rng.integers(0, g + 1, (1024, Dd)).astype(np.float32) * h).astype(np.float32)  # bucket corners
+    pts += [corners, np.nextafter(corners, np.float32(1e30)), np.nextafter(corners, np.float32(-1e30))]
+    edge = corners.copy(); edge[:, 0] = (rng.random(1024) * span[0] + lo[0]).astype(np.float32)    # on bucket edges
+    pts.append(edge)
+    pts.append((rng.standard_normal((128, Dd)) * 100 * max(scale, 1.0)).astype(np.float32))        # far outside
+    sp = np.zeros((8, Dd), np.float32)
+    sp[0, 0], sp[1, 0], sp[2, 0], sp[3, -1], sp[4, :], sp[5, :], sp[6, :], sp[7, :] = np.nan, np.inf, -np.inf, np.nan, 1e30, -1e30, 3e38, 1e-40
+    pts.append(sp)
+    desc = np.concatenate(pts).astype(np.float32)
+    ref = co.cells(desc, cent)
+    got = N(_native.cells(T(desc, dev), cent_t, None))
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} of {len(ref)} rows differ, first at {np.nonzero(got != ref)[0][:8]}"
+    assert np.array_equal(N(_native.cells(T(desc, dev), cent_t, None, allow_index=False)), ref)      # brute-force kernel, same inputs
+
+
 @pytest.mark.parametrize("K,Dd,B", [(5000, 32, 4096), (50000, 32, 8192), (2000, 16, 1000), (1024, 8, 300), (3333, 24, 129), (1500, 31, 777)])
 def test_cells_tensor_core_path(dev, co, K, Dd, B):
     """tcgen05 TF32 pass + exact FP32 re-rank == brute-force argmin of the reference expression, bit for bit:
