@@ -26,6 +26,7 @@ extern "C" {
 #define QDX_ERR_BAD_CELL (-4)          /* cell index out of range handed to qdx_offer_cells */
 #define QDX_ERR_BAD_INDEX (-5)         /* winner index outside the offspring buffer handed to qdx_commit */
 #define QDX_ERR_PEER_TIMEOUT (-6)      /* a peer's keys did not arrive within 2 s (peer-memory exchange) */
+#define QDX_ERR_INTERNAL (-7)          /* an in-kernel wait between CTAs timed out (never expected; reported instead of hanging) */
 
 /* task ids of the fused scoring functions */
 #define QDX_TASK_ID_NONE (-1)

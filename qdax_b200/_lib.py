@@ -20,6 +20,7 @@ ERRORS = {
     -4: "QDX_ERR_BAD_CELL: cell index out of range",
     -5: "QDX_ERR_BAD_INDEX: winner index outside the offspring buffer",
     -6: "QDX_ERR_PEER_TIMEOUT: a peer's keys did not arrive (peer-memory exchange)",
+    -7: "QDX_ERR_INTERNAL: an in-kernel wait between CTAs timed out",
 }
 
 

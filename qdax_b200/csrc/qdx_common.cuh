@@ -49,6 +49,10 @@ struct QdxWorkspace {
     int32_t part_add[QDX_MAX_COMMIT_CTAS];
     int32_t part_nan[QDX_MAX_COMMIT_CTAS];
     int32_t part_new[QDX_MAX_COMMIT_CTAS];      // cells that turned from empty to occupied in this commit
+    // streaming commit (qdx_commit.cu): per-CTA count of occupied cells, tagged with the launch sequence number
+    unsigned long long occ_pub[QDX_MAX_COMMIT_CTAS];
+    uint32_t commit_seq;
+    uint32_t pad1;
 };
 
 __host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

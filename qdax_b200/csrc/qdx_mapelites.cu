@@ -1054,6 +1054,24 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, c
     return 0;
 }
 
+// warp-per-cell commit kernel, ordinary launch: fallback of qdx_commit (qdx_commit.cu) when a cooperative launch or the
+// 16-byte row alignment of the bulk-copy path is not available
+int qdx_launch_commit_generic(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
+               const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
+               float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
+               int32_t mode, cudaStream_t stream) {
+    if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
+    if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
+    int64_t ctas = (K + 7) / 8;                 // one warp per cell, 8 warps per CTA, grid-stride beyond one wave
+    if (ctas > QDX_COMMIT_CTAS) ctas = QDX_COMMIT_CTAS;
+    if (ctas < 1) ctas = 1;
+    qdx_commit_kernel<<<(unsigned)ctas, 256, 0, stream>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
+                                                            idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
+                                                            qd_offset, metrics_out4, added_cells, mode);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" {
 
 int qdx_version(void) { return 100; }
@@ -1208,22 +1226,6 @@ int qdx_offer_cells(const int32_t* cells, const float* fitness, int64_t B, int64
     if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
     if (B == 0) return 0;
     qdx_offer_kernel<<<(unsigned)((B + 255) / 256), 256, 0, S(stream)>>>(cells, fitness, B, K, ws, rep_fitness, idx_base, first_wins);
-    QDX_CHECK_LAUNCH();
-    return 0;
-}
-
-int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
-               const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
-               float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
-               int32_t mode, void* stream) {
-    if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
-    if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
-    int64_t ctas = (K + 7) / 8;                 // one warp per cell, 8 warps per CTA, grid-stride beyond one wave
-    if (ctas > QDX_COMMIT_CTAS) ctas = QDX_COMMIT_CTAS;
-    if (ctas < 1) ctas = 1;
-    qdx_commit_kernel<<<(unsigned)ctas, 256, 0, S(stream)>>>(ws, K, (int32_t)D, desc_dim, off_genotypes, off_fitness, off_desc,
-                                                            idx_base, B, first_wins, rep_genotypes, rep_fitness, rep_desc,
-                                                            qd_offset, metrics_out4, added_cells, mode);
     QDX_CHECK_LAUNCH();
     return 0;
 }

@@ -399,7 +399,11 @@ def test_add_golden_injected(dev, golden, tb):
     assert np.array_equal(N(new.descriptors), g[f"S_add_{tb}_d"])
 
 
-@pytest.mark.parametrize("B,K,D,levels", [(50000, 10000, 100, 5), (100, 10000, 100, 1000), (65536, 100, 8, 3), (1, 4, 4, 1), (4096, 2500, 12, 2)])
+# shapes of the streaming commit: K = 14400 leaves empty trailing blocks, 57600 / 250000 need several 128-cell slabs per CTA,
+# D = 1040 rows travel in two bulk pieces, D = 6 / 1 take the per-lane copy (rows not 16-byte multiples)
+@pytest.mark.parametrize("B,K,D,levels", [(50000, 10000, 100, 5), (100, 10000, 100, 1000), (65536, 100, 8, 3), (1, 4, 4, 1), (4096, 2500, 12, 2),
+                                          (3000, 14400, 8, 50), (20000, 57600, 4, 10), (30000, 250000, 4, 10), (600, 100, 1040, 4),
+                                          (500, 100, 6, 4), (300, 64, 1, 3)])
 @pytest.mark.parametrize("tb", ["first", "last"])
 def test_add_injected_random(dev, co, B, K, D, levels, tb):
     """Injected identical offspring: cells, insertion decisions and the resulting repertoire are bit-exact,
@@ -427,6 +431,11 @@ def test_add_injected_random(dev, co, B, K, D, levels, tb):
     assert np.array_equal(N(new.genotypes), G)
     assert np.array_equal(N(new.fitnesses).ravel().view(np.uint32), F.view(np.uint32))   # bit pattern: -0.0 vs +0.0 too
     assert np.array_equal(N(new.descriptors), Dn)
+    # the commit kernel left the parent-selection tables of the NEXT generation in the workspace (no prepare launch)
+    if not np.isnan(F).any():
+        from qdax_b200.core.emitters.repertoire_selectors.uniform_selector import UniformSelector
+        assert new._workspace().sel_valid
+        assert np.array_equal(N(UniformSelector().select_indices(new, jr.key(B + 1), 3000)), co.select_indices(F, jr.key(B + 1), 3000))
     # idempotence: re-adding the repertoire's own contents changes nothing
     occ = np.isfinite(F) | (F == np.inf)
     again = new.add(T(G[occ], dev), T(Dn[occ], dev), T(F[occ], dev))
