@@ -32,7 +32,13 @@ namespace {
 constexpr int CW = QDX_COMMIT_CW;      // warps per CTA
 constexpr int NST = QDX_COMMIT_NST;    // ring stages per warp
 constexpr int LEAD = QDX_COMMIT_LEAD;  // loads run this many jobs ahead of the stores
-constexpr int CHUNK = 4096;        // bytes per stage (a row of D <= 1024 floats in one piece; longer rows in pieces)
+#ifndef QDX_COMMIT_CHUNK
+#define QDX_COMMIT_CHUNK 4096
+#endif
+#ifndef QDX_COMMIT_EXP
+#define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
+#endif
+constexpr int CHUNK = QDX_COMMIT_CHUNK;        // bytes per stage (a row of D <= 1024 floats in one piece; longer rows in pieces)
 constexpr int MAX_SLABS = 64;      // occupancy ballots kept in shared memory for the list pass (block <= 8192 cells)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,10 +95,8 @@ struct CommitParams {
 __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const CommitParams p) {
     extern __shared__ __align__(128) unsigned char s_stage[];        // [CW][NST][CHUNK]
     __shared__ uint64_t s_bar[CW * NST];
-    __shared__ int64_t s_src[CW * 32];
-    __shared__ int32_t s_cell[CW * 32];
     __shared__ uint32_t s_occ[MAX_SLABS * CW];
-    __shared__ int32_t s_n, s_base;
+    __shared__ int32_t s_base;
     __shared__ double s_sum[CW]; __shared__ float s_max[CW]; __shared__ int s_cnt[CW], s_nan[CW], s_add[CW];
     __shared__ bool s_last;
 
@@ -108,6 +112,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
     if ((int)blockIdx.x == nblk) {
         if (tail) {                                           // all threads collect the counts, thread 0 builds the segments
             int part = 0;
+#pragma unroll 4
             for (int b = tid; b < nblk; b += CW * 32) part += (int)wait_count(ws, b, seq);
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0) s_cnt[wid] = part;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             __syncthreads();
         }
     } else {
-        const int64_t per_cta = (p.K + nblk - 1) / nblk;          // equal blocks: every resident CTA streams the same share
+        const int64_t per_cta = (p.K + nblk - 1) / nblk;          // contiguous block of cells of this CTA
         const int64_t c_lo = (int64_t)blockIdx.x * per_cta < p.K ? (int64_t)blockIdx.x * per_cta : p.K;
         const int64_t c_hi = c_lo + per_cta < p.K ? c_lo + per_cta : p.K;
         const bool keep_bits = (c_hi - c_lo + CW * 32 - 1) / (CW * 32) <= MAX_SLABS;
@@ -128,39 +133,14 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             for (int s = 0; s < CW * NST; ++s) mbar_init(&s_bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        // ---- pass 0: how many of my cells are occupied after this commit?  (coalesced keys + fitness, L2-resident)
-        const bool one_slab = c_hi > c_lo && c_hi - c_lo <= CW * 32;     // then the main pass itself yields the count
-        if (tail && c_hi <= c_lo && tid == 0)                 // empty block (K not a multiple of the block size)
-            *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = (unsigned long long)seq << 32;
-        if (tail && !one_slab && c_hi > c_lo) {
-            int c0 = 0;
-            for (int64_t c = c_lo + tid; c < c_hi; c += CW * 32) {
-                const unsigned long long key = __ldcg(keytab + c);
-                bool win = key != 0ull && !qdx_key_is_nan(key);
-                if (win && mode == 0) { const int64_t i = (int64_t)qdx_key_index(key, p.first_wins) - (int64_t)p.idx_base; win = i >= 0 && i < p.B; }
-                c0 += (win || __ldcg(p.rep_f + c) != -INFINITY);
-            }
-            for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-            if (lane == 0) s_cnt[wid] = c0;
-            __syncthreads();
-            if (tid == 0) {
-                int t = 0;
-                for (int w = 0; w < CW; ++w) t += s_cnt[w];
-                *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
-            }
-        }
-        __syncthreads();                                      // mbarriers initialised, s_cnt free again
+        int32_t* job_cell = qdx_ws_jobs(p.ws, p.K);              // global list of changed cells: (cell, source row)
+        int32_t* job_src = job_cell + p.K;
 
-        // ---- main pass, 128 cells per slab: thread = cell, then the warps stream the winners' rows
-        const uint32_t rowbytes = (uint32_t)p.D * 4u;
-        const bool bulk = (p.D & 3) == 0;
-        const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
-        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
-        uint32_t jq = 0;                                      // jobs this warp has pushed through its ring so far
-        int slab_i = 0;
+        // ---- phase 1, thread = cell: election result, fitness / descriptor, key reset, metrics, occupancy; the changed
+        // cells of the whole grid are appended to ONE global list (warp-aggregated atomics) so that phase 2 can deal the
+        // row copies out evenly -- winners per block vary, and so does the distance of an SM to the memory it reads
+        int occ_after = 0, slab_i = 0;
         for (int64_t slab = c_lo; slab < c_hi; slab += CW * 32, ++slab_i) {
-            if (tid == 0) s_n = 0;
-            __syncthreads();
             const int64_t c = slab + tid;
             const bool in = c < c_hi;
             const unsigned long long key = in ? __ldcg(keytab + c) : 0ull;
@@ -189,54 +169,83 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             }
             const unsigned ob = __ballot_sync(0xffffffffu, in && fcell != -INFINITY);
             if (keep_bits && lane == 0) s_occ[slab_i * CW + wid] = ob;
-            if (tail && one_slab && lane == 0) s_cnt[wid] = __popc(ob);
+            occ_after += __popc(ob);
             const unsigned wb = __ballot_sync(0xffffffffu, i >= 0);
-            int base = 0;
-            if (lane == 0 && wb) base = atomicAdd(&s_n, __popc(wb));
+            unsigned base = 0;
+            if (lane == 0 && wb) base = atomicAdd(&ws->job_count, (unsigned)__popc(wb));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (i >= 0) { const int pos = base + __popc(wb & ((1u << lane) - 1u)); s_cell[pos] = (int32_t)(c - slab); s_src[pos] = i; }
-            __syncthreads();
-            if (tail && one_slab && tid == 0) {
-                int t = 0;
-                for (int w = 0; w < CW; ++w) t += s_cnt[w];
-                *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
+            if (i >= 0) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
+        }
+        if (lane == 0) s_cnt[wid] = occ_after;                // identical on every lane of the warp
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < CW; ++w) t += s_cnt[w];
+            if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
+            __threadfence();
+            atomicAdd(&ws->cta_arrived, 1u);
+            // ---- grid barrier (all CTAs are co-resident: cooperative launch): the job list is complete
+            unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
+                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
             }
-            const int n = s_n;
-            const int n_e = n > wid ? (n - wid + CW - 1) / CW : 0;        // entries wid, wid + CW, ...
+            __threadfence();
+        }
+        __syncthreads();
+
+        // ---- phase 2: warp g of the grid streams jobs g, g + G, g + 2G, ... through its ring of shared-memory stages
+        const unsigned njobs_all = *(volatile unsigned*)&ws->job_count;
+        const uint32_t rowbytes = (uint32_t)p.D * 4u;
+        const bool bulk = (p.D & 3) == 0;
+        const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
+        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
+        const unsigned g = blockIdx.x * CW + wid, G = (unsigned)nblk * CW;
+        uint32_t jq = 0;                                      // pieces this warp has pushed through its ring so far
+        for (unsigned j0 = g; j0 < (QDX_COMMIT_EXP == 2 ? 0u : njobs_all); j0 += 32u * G) {      // up to 32 jobs per round: lane l holds job j0 + l G
+            const unsigned jmine = j0 + (unsigned)lane * G;
+            const int32_t my_cell = jmine < njobs_all ? __ldcg(job_cell + jmine) : 0;
+            const int32_t my_src = jmine < njobs_all ? __ldcg(job_src + jmine) : 0;
+            const int n_e = (int)((njobs_all - j0 + G - 1) / G) < 32 ? (int)((njobs_all - j0 + G - 1) / G) : 32;
             if (bulk) {
-                if (lane == 0 && n_e > 0) {
-                    const int njobs = n_e * pieces;
-                    for (int t = 0; t < njobs + LEAD; ++t) {
-                        if (t >= LEAD) {                                  // row piece t - LEAD has landed: send it on
-                            const int j = t - LEAD;
+                const int np = n_e * pieces;
+                for (int t = 0; t < np + LEAD; ++t) {
+                    if (t >= LEAD) {                                  // piece t - LEAD has landed: send it on
+                        const int j = t - LEAD;
+                        const int e = j / pieces, pc = j % pieces;
+                        const int32_t cell = __shfl_sync(0xffffffffu, my_cell, e);
+                        if (lane == 0) {
                             const uint32_t q = jq + (uint32_t)j;
-                            const int e = wid + CW * (j / pieces), pc = j % pieces;
                             const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
                             mbar_wait(&s_bar[wid * NST + (q % NST)], (q / NST) & 1u);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            bulk_s2g((char*)p.rep_g + ((slab + s_cell[e]) * (int64_t)p.D) * 4 + (int64_t)pc * CHUNK, my_stage + (q % NST) * CHUNK, bytes);
+                            if (QDX_COMMIT_EXP != 1) bulk_s2g((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK, my_stage + (q % NST) * CHUNK, bytes);
                         }
-                        if (t < njobs) {                                  // stage free again? (its previous store has read it)
+                    }
+                    if (t < np) {                                     // stage free again? (its previous store has read it)
+                        const int e = t / pieces, pc = t % pieces;
+                        const int32_t src = __shfl_sync(0xffffffffu, my_src, e);
+                        if (lane == 0) {
                             const uint32_t q = jq + (uint32_t)t;
-                            const int e = wid + CW * (t / pieces), pc = t % pieces;
                             const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
                             asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");
                             mbar_expect_tx(&s_bar[wid * NST + (q % NST)], bytes);
-                            bulk_g2s(my_stage + (q % NST) * CHUNK, (const char*)p.off_g + (s_src[e] * (int64_t)p.D) * 4 + (int64_t)pc * CHUNK, bytes,
+                            bulk_g2s(my_stage + (q % NST) * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes,
                                      &s_bar[wid * NST + (q % NST)]);
                         }
                     }
-                    jq += (uint32_t)njobs;
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
+                jq += (uint32_t)np;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
             } else {                                                      // D not a multiple of 4: plain per-lane copy
-                for (int k = 0; k < n_e; ++k) {
-                    const int e = wid + CW * k;
-                    const float* srow = p.off_g + s_src[e] * (int64_t)p.D; float* drow = p.rep_g + (slab + s_cell[e]) * (int64_t)p.D;
+                for (int e = 0; e < n_e; ++e) {
+                    const int32_t cell = __shfl_sync(0xffffffffu, my_cell, e), src = __shfl_sync(0xffffffffu, my_src, e);
+                    const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
                     for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
                 }
             }
-            __syncthreads();
         }
         if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             if (tid == 0) s_base = 0;
             __syncthreads();
             int part = 0;
+#pragma unroll 4
             for (int b = tid; b < (int)blockIdx.x; b += CW * 32) part += (int)wait_count(ws, b, seq);
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0 && part) atomicAdd(&s_base, part);
@@ -274,8 +284,6 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             }
         }
     }
-    if (!tail) return;
-
     // ---- metrics: CTAs publish partials, the last CTA to finish sums them in CTA order (deterministic)
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -317,8 +325,10 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
         out[1] = nn ? NAN : m;                                     // max_fitness (:95)
         out[2] = 100.0f * __fdiv_rn((float)n, (float)p.K);         // coverage   (:94)
         out[3] = (float)a;                                         // offspring inserted by this call
-        for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (p.metrics_out) p.metrics_out[j] = out[j]; }
+        if (tail) for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (p.metrics_out) p.metrics_out[j] = out[j]; }
         ws->ticket = 0u;
+        ws->cta_arrived = 0u;
+        ws->job_count = 0u;
         ws->commit_seq = seq;
         if (mode == 2 && ws->xchg_nranks > 0) {                    // peer-memory exchange: next generation, other key table
             uint32_t* ep = (uint32_t*)((char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET);

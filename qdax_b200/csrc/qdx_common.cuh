@@ -52,6 +52,8 @@ struct QdxWorkspace {
     // streaming commit (qdx_commit.cu): per-CTA count of occupied cells, tagged with the launch sequence number
     unsigned long long occ_pub[QDX_MAX_COMMIT_CTAS];
     uint32_t commit_seq;
+    uint32_t cta_arrived;   // grid barrier of the streaming commit (reset by its last CTA)
+    uint32_t job_count;     // entries of the global list of changed cells (reset by the last CTA)
     uint32_t pad1;
 };
 
@@ -61,9 +63,13 @@ __host__ __device__ inline size_t qdx_ws_keytab_offset(int64_t K) {
     return qdx_align_up(qdx_ws_occ_offset() + sizeof(int32_t) * (size_t)K, 256);
 }
 #define QDX_MAX_RANKS 64      // generation keys of up to 64 ranks ride in the tail of the key table (8 slots each)
-__host__ __device__ inline size_t qdx_ws_total_bytes(int64_t K) {
+__host__ __device__ inline size_t qdx_ws_jobs_offset(int64_t K) {      // (cell, source row) int32 pairs of the streaming commit
     return qdx_align_up(qdx_ws_keytab_offset(K) + sizeof(unsigned long long) * (size_t)(K + 8 * QDX_MAX_RANKS), 256);
 }
+__host__ __device__ inline size_t qdx_ws_total_bytes(int64_t K) {
+    return qdx_align_up(qdx_ws_jobs_offset(K) + 2 * sizeof(int32_t) * (size_t)K, 256);
+}
+__host__ __device__ inline int32_t* qdx_ws_jobs(void* ws, int64_t K) { return (int32_t*)((char*)ws + qdx_ws_jobs_offset(K)); }
 __host__ __device__ inline int32_t* qdx_ws_occ(void* ws) { return (int32_t*)((char*)ws + qdx_ws_occ_offset()); }
 // Peer-memory exchange buffer of one rank (cudaMalloc'ed by qdx_xchg_create, mapped into every peer with cudaIpc):
 //   [0, 512)             arrival flags: flag[r] = epoch + 1 once rank r's keys of that epoch have landed here

@@ -8,7 +8,8 @@ from qdax_b200 import _native
 dev = torch.device("cuda:0")
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6650.0
 out = {}
-for name, (K, D, Dd, B) in {"c4_cold_start": (50000, 1000, 32, 65536), "c3_cold_start": (10000, 100, 2, 1 << 20)}.items():
+for name, (K, D, Dd, B) in {"c4_cold_start": (50000, 1000, 32, 65536), "c4_cold_start_b262144": (50000, 1000, 32, 262144),
+                            "c3_cold_start": (10000, 100, 2, 1 << 20)}.items():
     rng = np.random.default_rng(0)
     cent = torch.from_numpy(rng.random((K, Dd)).astype(np.float32)).to(dev)
     g = torch.rand(B, D, device=dev); d = torch.rand(B, Dd, device=dev); f = torch.randn(B, device=dev)
