@@ -6,14 +6,18 @@
 // rows never touch registers: one elected lane per warp drives a 4-stage ring of shared-memory buffers with the
 // bulk-copy engine -- cp.async.bulk global->shared (completion on an mbarrier), then cp.async.bulk shared->global --
 // two loads and two stores of up to 4 KB in flight per warp, 12 warps per SM.  Everything around the row traffic is
-// arranged so that nothing serial is left behind it:
-//   * cells are split into contiguous blocks, one per CTA (cooperative launch: all CTAs are co-resident); thread = cell
-//     for the coalesced key / fitness pass, winners compacted into a shared list, warps take them round-robin;
-//   * every CTA first publishes how many of its cells are occupied after this commit; later it derives its offset in
-//     the ordered occupied-cell list from its predecessors' counts and writes its slice (distributed scan, no tail);
-//   * one extra CTA owns nothing but the selection segments: it sums all counts and rebuilds them (qdx_build_sel, a
-//     serial ~8 us computation when the number of occupied cells changed) while the others stream rows;
-//   * the last CTA to finish (ticket) only reduces <= 593 partial metrics.
+// arranged so that nothing serial is left behind it (per-phase globaltimer stamps: -DQDX_COMMIT_TRACE=1):
+//   * phase 1, thread = cell over contiguous blocks of cells (cooperative launch: all CTAs are co-resident): coalesced
+//     key / fitness pass, winner descriptors copied with all loads ahead of all stores, changed cells appended to ONE
+//     grid-wide job list; every CTA then publishes its partial metrics and its count of occupied cells;
+//   * grid barrier (one fence, one atomic, one spin per CTA);
+//   * phase 2, the row copies, by guided self-scheduling over the job list (static first batch, then batches from a
+//     grid-wide counter that shrink with the work left), so the SMs run out of work together although their distance
+//     to the memory differs; measured streaming rate = the HBM copy peak;
+//   * a service CTA that owns no cells sums the published metrics and rebuilds the selection segments (qdx_build_sel, a
+//     serial ~8 us computation when the number of occupied cells changed) while the others stream;
+//   * afterwards every CTA writes its slice of the ordered occupied-cell list (offset = sum of its predecessors'
+//     counts, one batched read) and the last CTA to finish (ticket) re-arms the workspace counters.
 #include <cstring>
 #include "qdx_common.cuh"
 #include "../../include/qdx.h"
@@ -31,7 +35,19 @@ namespace {
 #endif
 constexpr int CW = QDX_COMMIT_CW;      // warps per CTA
 constexpr int NST = QDX_COMMIT_NST;    // ring stages per warp
-constexpr int LEAD = QDX_COMMIT_LEAD;  // loads run this many jobs ahead of the stores
+constexpr int LEAD = QDX_COMMIT_LEAD;  // loads run this many pieces ahead of the stores
+#ifndef QDX_COMMIT_JB
+#define QDX_COMMIT_JB 8
+#endif
+#ifndef QDX_COMMIT_GS
+#define QDX_COMMIT_GS 2
+#endif
+#ifndef QDX_COMMIT_GD
+#define QDX_COMMIT_GD 2
+#endif
+constexpr unsigned GS = QDX_COMMIT_GS;  // static first batch = list / (GS * warps of the grid)
+constexpr unsigned GD = QDX_COMMIT_GD;  // dynamic batch = remaining list / (GD * warps of the grid)
+constexpr int JB = QDX_COMMIT_JB;      // most list entries (changed cells) per grab from the grid-wide counter (<= 32)
 #ifndef QDX_COMMIT_CHUNK
 #define QDX_COMMIT_CHUNK 4096
 #endif
@@ -39,6 +55,17 @@ constexpr int LEAD = QDX_COMMIT_LEAD;  // loads run this many jobs ahead of the 
 #define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
 #endif
 constexpr int CHUNK = QDX_COMMIT_CHUNK;        // bytes per stage (a row of D <= 1024 floats in one piece; longer rows in pieces)
+#ifndef QDX_COMMIT_TRACE
+#define QDX_COMMIT_TRACE 0    // timing experiments only: per-phase globaltimer stamps (tools/time_insert.py --trace)
+#endif
+#if QDX_COMMIT_TRACE
+__device__ unsigned long long g_commit_trace[8];
+#define QDX_TRACE_MIN(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMin(&g_commit_trace[i], t_); } } while (0)
+#define QDX_TRACE_MAX(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax(&g_commit_trace[i], t_); } } while (0)
+#else
+#define QDX_TRACE_MIN(i)
+#define QDX_TRACE_MAX(i)
+#endif
 constexpr int MAX_SLABS = 64;      // occupancy ballots kept in shared memory for the list pass (block <= 8192 cells)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,11 +109,76 @@ __device__ __forceinline__ uint32_t wait_count(QdxWorkspace* ws, int b, uint32_t
     }
 }
 
+// Per-thread partial sum of the occupied counts of CTAs [0, limit): the first reads go out together (one memory round
+// trip for up to 4 counts per thread); only a count that has not been published yet is waited for.
+__device__ __forceinline__ int sum_counts(QdxWorkspace* ws, int limit, uint32_t seq, int t, int nt) {      // thread t of nt
+    int part = 0;
+    for (int b0 = t; b0 < limit; b0 += 4 * nt) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + j * nt;
+            v[j] = b < limit ? *(volatile unsigned long long*)&ws->occ_pub[b] : ((unsigned long long)seq << 32);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + j * nt;
+            if ((uint32_t)(v[j] >> 32) != seq) v[j] = (unsigned long long)wait_count(ws, b, seq);
+            part += (int)(uint32_t)v[j];
+        }
+    }
+    return part;
+}
+
 struct CommitParams {
     void* ws; int64_t K; int32_t D; int32_t Dd;
     const float* off_g; const float* off_f; const float* off_d; uint32_t idx_base; int64_t B; int32_t first_wins;
     float* rep_g; float* rep_f; float* rep_d; float qd_offset; float* metrics_out; int32_t* added_cells; int32_t mode;
 };
+
+// One winner descriptor row, off_d[i] -> rep_d[c]: all loads first, then all stores (a load / store pair per element
+// would serialise on the possible aliasing of the two arrays: one memory round trip per element).
+__device__ __forceinline__ void copy_desc(const float* __restrict__ src, float* __restrict__ dst, int Dd, bool vec4) {
+    if (vec4) {
+        for (int d0 = 0; d0 < Dd; d0 += 32) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (d0 + 4 * j < Dd) v[j] = __ldg((const float4*)(src + d0) + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (d0 + 4 * j < Dd) ((float4*)(dst + d0))[j] = v[j];
+        }
+    } else {
+        for (int d0 = 0; d0 < Dd; d0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (d0 + j < Dd) v[j] = __ldg(src + d0 + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (d0 + j < Dd) dst[d0 + j] = v[j];
+        }
+    }
+}
+
+// Sum of the per-CTA partial metrics in CTA order (deterministic), by all threads of one CTA; result valid on thread 0.
+struct MetricsAcc { double s; float m; int n, nn, a; };
+__device__ __forceinline__ MetricsAcc reduce_partials(QdxWorkspace* ws, int nparts, double* s_sum, float* s_max, int* s_cnt, int* s_nan, int* s_add) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+    for (int b = tid; b < nparts; b += CW * 32) {
+        s += *(volatile double*)&ws->part_sum[b]; m = fmaxf(m, *(volatile float*)&ws->part_max[b]);
+        n += *(volatile int32_t*)&ws->part_cnt[b]; nn |= *(volatile int32_t*)&ws->part_nan[b]; a += *(volatile int32_t*)&ws->part_add[b];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        n += __shfl_xor_sync(0xffffffffu, n, o); nn |= __shfl_xor_sync(0xffffffffu, nn, o); a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    __syncthreads();
+    if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; }
+    __syncthreads();
+    MetricsAcc r{0.0, -INFINITY, 0, 0, 0};
+    if (tid == 0)
+        for (int w = 0; w < CW; ++w) { r.s += s_sum[w]; r.m = fmaxf(r.m, s_max[w]); r.n += s_cnt[w]; r.nn |= s_nan[w]; r.a += s_add[w]; }
+    return r;
+}
 
 // mode 0: commit winners whose offspring rows are in off_* (index = global idx - idx_base), reset keys, metrics, tables
 // mode 1: stage -- copy only the winners owned by [idx_base, idx_base + B) into rep_* (= staging rows by cell), keep
@@ -95,50 +187,60 @@ struct CommitParams {
 __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const CommitParams p) {
     extern __shared__ __align__(128) unsigned char s_stage[];        // [CW][NST][CHUNK]
     __shared__ uint64_t s_bar[CW * NST];
+    __shared__ unsigned long long s_dst[CW * NST];                   // destination of the piece sitting in each stage
+    __shared__ uint32_t s_bytes[CW * NST];
     __shared__ uint32_t s_occ[MAX_SLABS * CW];
     __shared__ int32_t s_base;
-    __shared__ double s_sum[CW]; __shared__ float s_max[CW]; __shared__ int s_cnt[CW], s_nan[CW], s_add[CW];
-    __shared__ bool s_last;
+    __shared__ double s_sum[CW]; __shared__ float s_max[CW]; __shared__ int s_cnt[CW], s_nan[CW], s_add[CW], s_occn[CW];
 
     QdxWorkspace* ws = (QdxWorkspace*)p.ws;
     unsigned long long* keytab = qdx_ws_keytab(p.ws, p.K);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int mode = p.mode;
     const bool tail = mode != 1;
-    const int nblk = (int)gridDim.x - 1;                     // streaming CTAs; CTA nblk only builds the selection segments
+    const int nblk = (int)gridDim.x - 1;                     // streaming CTAs; CTA nblk is the service CTA
     const uint32_t seq = *(volatile uint32_t*)&ws->commit_seq + 1u;     // tag of this launch in occ_pub
-    double sum = 0.0; float mx = -INFINITY; int cnt = 0, nan = 0, added = 0;
+    QDX_TRACE_MIN(0);                                         // first CTA starts
 
     if ((int)blockIdx.x == nblk) {
-        if (tail) {                                           // all threads collect the counts, thread 0 builds the segments
-            int part = 0;
-#pragma unroll 4
-            for (int b = tid; b < nblk; b += CW * 32) part += (int)wait_count(ws, b, seq);
+        // ---- service CTA: everything that needs the whole grid's phase-1 results but not the row traffic -- metrics
+        // and the selection segments of the next generation -- runs here, behind the streaming of the other CTAs
+        if (tail) {
+            int part = sum_counts(ws, nblk, seq, tid, CW * 32);
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (lane == 0) s_cnt[wid] = part;
-            __syncthreads();
+            if (lane == 0) s_occn[wid] = part;
+            __threadfence();                                  // the partial metrics were published before the counts
+            const MetricsAcc r = reduce_partials(ws, nblk, s_sum, s_max, s_cnt, s_nan, s_add);
             if (tid == 0) {
+                float out[4];
+                out[0] = (float)r.s + p.qd_offset * (float)r.n;            // qd_score   (metrics.py:92-93)
+                out[1] = r.nn ? NAN : r.m;                                  // max_fitness (:95)
+                out[2] = 100.0f * __fdiv_rn((float)r.n, (float)p.K);        // coverage   (:94)
+                out[3] = (float)r.a;                                        // offspring inserted by this call
+                for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (p.metrics_out) p.metrics_out[j] = out[j]; }
+                QDX_TRACE_MAX(7);                                           // metrics written
                 int M = 0;
-                for (int w = 0; w < CW; ++w) M += s_cnt[w];
+                for (int w = 0; w < CW; ++w) M += s_occn[w];
                 if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
             }
-            __syncthreads();
         }
     } else {
         const int64_t per_cta = (p.K + nblk - 1) / nblk;          // contiguous block of cells of this CTA
         const int64_t c_lo = (int64_t)blockIdx.x * per_cta < p.K ? (int64_t)blockIdx.x * per_cta : p.K;
         const int64_t c_hi = c_lo + per_cta < p.K ? c_lo + per_cta : p.K;
         const bool keep_bits = (c_hi - c_lo + CW * 32 - 1) / (CW * 32) <= MAX_SLABS;
+        const bool vec4 = (p.Dd & 3) == 0 && ((((uintptr_t)p.off_d) | ((uintptr_t)p.rep_d)) & 15u) == 0;
         if (tid == 0) {
+            s_base = 0;
             for (int s = 0; s < CW * NST; ++s) mbar_init(&s_bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         int32_t* job_cell = qdx_ws_jobs(p.ws, p.K);              // global list of changed cells: (cell, source row)
         int32_t* job_src = job_cell + p.K;
+        double sum = 0.0; float mx = -INFINITY; int cnt = 0, nan = 0, added = 0;
 
         // ---- phase 1, thread = cell: election result, fitness / descriptor, key reset, metrics, occupancy; the changed
-        // cells of the whole grid are appended to ONE global list (warp-aggregated atomics) so that phase 2 can deal the
-        // row copies out evenly -- winners per block vary, and so does the distance of an SM to the memory it reads
+        // cells of the whole grid are appended to ONE global list (warp-aggregated atomics) that phase 2 deals out
         int occ_after = 0, slab_i = 0;
         for (int64_t slab = c_lo; slab < c_hi; slab += CW * 32, ++slab_i) {
             const int64_t c = slab + tid;
@@ -156,9 +258,9 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             if (in) {
                 if (i >= 0) {
                     fcell = __ldg(p.off_f + i);
+                    copy_desc(p.off_d + i * p.Dd, p.rep_d + c * p.Dd, p.Dd, vec4);
                     p.rep_f[c] = fcell;
                     if (p.added_cells) p.added_cells[c] = (int32_t)i;
-                    for (int d = 0; d < p.Dd; ++d) p.rep_d[c * p.Dd + d] = __ldg(p.off_d + i * p.Dd + d);
                     ++added;
                 } else if (tail) {
                     fcell = __ldcg(p.rep_f + c);
@@ -176,86 +278,130 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             base = __shfl_sync(0xffffffffu, base, 0);
             if (i >= 0) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
         }
-        if (lane == 0) s_cnt[wid] = occ_after;                // identical on every lane of the warp
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int w = 0; w < CW; ++w) t += s_cnt[w];
-            if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
-            __threadfence();
-            atomicAdd(&ws->cta_arrived, 1u);
-            // ---- grid barrier (all CTAs are co-resident: cooperative launch): the job list is complete
-            unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
-                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
+        // ---- this CTA's partial metrics and occupied count, published BEFORE the grid barrier: the service CTA sums them
+        // while the rows stream
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nan |= __shfl_xor_sync(0xffffffffu, nan, o); added += __shfl_xor_sync(0xffffffffu, added, o);
+        }
+        if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; s_occn[wid] = occ_after; }
+        __syncthreads();                                      // the CTA's job-list entries and rows are ordered before thread 0's fence below
+        QDX_TRACE_MIN(1); QDX_TRACE_MAX(2);                   // first / last CTA done with phase 1
+        if (wid == 0) {
+            // ---- warp 0: publish this CTA's partial metrics and occupied count (the service CTA sums them while the rows
+            // stream), then the grid barrier (all CTAs are co-resident: cooperative launch): the job list is complete
+            if (lane == 0) {
+                int t = 0;
+                if (tail) {
+                    double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
+                    for (int w = 0; w < CW; ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; t += s_occn[w]; }
+                    ws->part_sum[blockIdx.x] = s; ws->part_max[blockIdx.x] = m; ws->part_cnt[blockIdx.x] = n; ws->part_nan[blockIdx.x] = nn;
+                    ws->part_add[blockIdx.x] = a;
+                }
+                __threadfence();                              // ONE fence: partials + job list before the count and the arrival
+                if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
+                atomicAdd(&ws->cta_arrived, 1u);
+                unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
+                    unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
+                }
+                __threadfence();
             }
-            __threadfence();
         }
         __syncthreads();
+        QDX_TRACE_MAX(3);                                     // last CTA through the grid barrier
 
-        // ---- phase 2: warp g of the grid streams jobs g, g + G, g + 2G, ... through its ring of shared-memory stages
-        const unsigned njobs_all = *(volatile unsigned*)&ws->job_count;
+        // ---- phase 2: the row copies, dealt out in batches of list entries.  SMs differ in their distance to the memory
+        // they read and write, so a static deal leaves the slow ones streaming long after the fast ones are done (measured:
+        // first CTA done at 36 us, last at 49 us).  Guided self-scheduling instead: warp g of the grid starts on batch g
+        // (static, no atomic), every further batch comes from a grid-wide counter and shrinks with the work that is left
+        // (JB entries while plenty remain, 1 at the end), so the warps run out of work within a row or two of each other.
+        // The grab for the next batch is issued when a batch starts and consumed after its first row, and that batch's
+        // list entries are fetched by the lanes then -- both latencies sit behind row traffic already in flight.
+        const unsigned njobs = QDX_COMMIT_EXP == 2 ? 0u : *(volatile unsigned*)&ws->job_count;
         const uint32_t rowbytes = (uint32_t)p.D * 4u;
         const bool bulk = (p.D & 3) == 0;
         const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
-        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
         const unsigned g = blockIdx.x * CW + wid, G = (unsigned)nblk * CW;
-        uint32_t jq = 0;                                      // pieces this warp has pushed through its ring so far
-        for (unsigned j0 = g; j0 < (QDX_COMMIT_EXP == 2 ? 0u : njobs_all); j0 += 32u * G) {      // up to 32 jobs per round: lane l holds job j0 + l G
-            const unsigned jmine = j0 + (unsigned)lane * G;
-            const int32_t my_cell = jmine < njobs_all ? __ldcg(job_cell + jmine) : 0;
-            const int32_t my_src = jmine < njobs_all ? __ldcg(job_src + jmine) : 0;
-            const int n_e = (int)((njobs_all - j0 + G - 1) / G) < 32 ? (int)((njobs_all - j0 + G - 1) / G) : 32;
-            if (bulk) {
-                const int np = n_e * pieces;
-                for (int t = 0; t < np + LEAD; ++t) {
-                    if (t >= LEAD) {                                  // piece t - LEAD has landed: send it on
-                        const int j = t - LEAD;
-                        const int e = j / pieces, pc = j % pieces;
-                        const int32_t cell = __shfl_sync(0xffffffffu, my_cell, e);
-                        if (lane == 0) {
-                            const uint32_t q = jq + (uint32_t)j;
+        unsigned J0 = (njobs + GS * G - 1u) / (GS * G);                     // static first batch: about half of the list
+        J0 = J0 < 1u ? 1u : (J0 > (unsigned)JB ? (unsigned)JB : J0);
+        const unsigned dyn_base = G * J0;
+        bool dyn = dyn_base < njobs;
+        unsigned est = dyn_base;                                            // lane 0: where the counter stood at the last grab
+        unsigned cur_base = g * J0, cur_n = cur_base < njobs ? (njobs - cur_base < J0 ? njobs - cur_base : J0) : 0u;
+        int32_t my_cell = 0, my_src = 0;
+        if ((unsigned)lane < cur_n) { my_cell = __ldcg(job_cell + cur_base + lane); my_src = __ldcg(job_src + cur_base + lane); }
+        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
+        uint64_t* bars = &s_bar[wid * NST];
+        unsigned long long* sdst = &s_dst[wid * NST];
+        uint32_t* sby = &s_bytes[wid * NST];
+        uint32_t ql = 0, qs = 0;                                            // lane 0: pieces loaded / stored so far (ring positions)
+        while (cur_n > 0u) {
+            unsigned nxt_base = 0xFFFFFFFFu, nxt_n = 0u;
+            if (dyn && lane == 0) {
+                const unsigned rem = njobs > est ? njobs - est : 0u;
+                unsigned want = rem / (GD * G);
+                want = want < 1u ? 1u : (want > (unsigned)JB ? (unsigned)JB : want);
+                nxt_base = dyn_base + atomicAdd(&ws->job_next, want);
+                nxt_n = want;
+            }
+            int32_t nx_cell = 0, nx_src = 0;
+            for (unsigned e = 0; e < cur_n; ++e) {
+                const int32_t cell = __shfl_sync(0xffffffffu, my_cell, (int)e), src = __shfl_sync(0xffffffffu, my_src, (int)e);
+                if (bulk) {
+                    if (lane == 0) {
+                        for (int pc = 0; pc < pieces; ++pc) {
+                            if (ql - qs >= (uint32_t)LEAD) {          // piece qs has been in flight long enough: send it on
+                                const uint32_t sl = qs % NST;
+                                mbar_wait(&bars[sl], (qs / NST) & 1u);
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
+                                ++qs;
+                            }
+                            const uint32_t sl = ql % NST;
                             const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
-                            mbar_wait(&s_bar[wid * NST + (q % NST)], (q / NST) & 1u);
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            if (QDX_COMMIT_EXP != 1) bulk_s2g((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK, my_stage + (q % NST) * CHUNK, bytes);
+                            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");   // stage free again
+                            sdst[sl] = (unsigned long long)((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK);
+                            sby[sl] = bytes;
+                            mbar_expect_tx(&bars[sl], bytes);
+                            bulk_g2s(my_stage + sl * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes, &bars[sl]);
+                            ++ql;
                         }
                     }
-                    if (t < np) {                                     // stage free again? (its previous store has read it)
-                        const int e = t / pieces, pc = t % pieces;
-                        const int32_t src = __shfl_sync(0xffffffffu, my_src, e);
-                        if (lane == 0) {
-                            const uint32_t q = jq + (uint32_t)t;
-                            const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
-                            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");
-                            mbar_expect_tx(&s_bar[wid * NST + (q % NST)], bytes);
-                            bulk_g2s(my_stage + (q % NST) * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes,
-                                     &s_bar[wid * NST + (q % NST)]);
-                        }
-                    }
-                }
-                jq += (uint32_t)np;
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            } else {                                                      // D not a multiple of 4: plain per-lane copy
-                for (int e = 0; e < n_e; ++e) {
-                    const int32_t cell = __shfl_sync(0xffffffffu, my_cell, e), src = __shfl_sync(0xffffffffu, my_src, e);
+                    __syncwarp();
+                } else {                                                  // D not a multiple of 4: plain per-lane copy
                     const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
                     for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
                 }
+                if (e == 0u && dyn) {
+                    nxt_base = __shfl_sync(0xffffffffu, nxt_base, 0); nxt_n = __shfl_sync(0xffffffffu, nxt_n, 0);
+                    est = nxt_base + nxt_n;
+                    if (nxt_base < njobs) {
+                        if (njobs - nxt_base < nxt_n) nxt_n = njobs - nxt_base;
+                        if ((unsigned)lane < nxt_n) { nx_cell = __ldcg(job_cell + nxt_base + lane); nx_src = __ldcg(job_src + nxt_base + lane); }
+                    } else { nxt_n = 0u; dyn = false; }
+                }
             }
+            cur_base = nxt_base; cur_n = nxt_n; my_cell = nx_cell; my_src = nx_src;
         }
-        if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-
-        // ---- my slice of the ordered occupied-cell list: offset = sum of the predecessors' counts
+        if (bulk && lane == 0) {
+            while (qs < ql) {
+                const uint32_t sl = qs % NST;
+                mbar_wait(&bars[sl], (qs / NST) & 1u);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
+                ++qs;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        QDX_TRACE_MIN(4); QDX_TRACE_MAX(5);                   // first / last CTA done streaming
+        // ---- my slice of the ordered occupied-cell list: offset = sum of the predecessors' counts (all published before
+        // the grid barrier, so this is one batched read; doing it before the barrier instead was measured 6-8 us slower --
+        // thousands of threads polling for counts delay the CTAs that still have to publish theirs)
         if (tail) {
-            if (tid == 0) s_base = 0;
-            __syncthreads();
-            int part = 0;
-#pragma unroll 4
-            for (int b = tid; b < (int)blockIdx.x; b += CW * 32) part += (int)wait_count(ws, b, seq);
+            int part = sum_counts(ws, (int)blockIdx.x, seq, tid, CW * 32);
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if (lane == 0 && part) atomicAdd(&s_base, part);
             __syncthreads();
@@ -284,55 +430,21 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             }
         }
     }
-    // ---- metrics: CTAs publish partials, the last CTA to finish sums them in CTA order (deterministic)
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nan |= __shfl_xor_sync(0xffffffffu, nan, o); added += __shfl_xor_sync(0xffffffffu, added, o);
-    }
-    __syncthreads();
-    if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; }
+    // ---- the last CTA to finish re-arms the workspace for the next launch
     __syncthreads();
     if (tid == 0) {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
-        for (int w = 0; w < CW; ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; }
-        ws->part_sum[blockIdx.x] = s; ws->part_max[blockIdx.x] = m; ws->part_cnt[blockIdx.x] = n; ws->part_nan[blockIdx.x] = nn;
-        ws->part_add[blockIdx.x] = a;
         __threadfence();
-        s_last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
-        for (unsigned b = tid; b < gridDim.x; b += CW * 32) {
-            s += *(volatile double*)&ws->part_sum[b]; m = fmaxf(m, *(volatile float*)&ws->part_max[b]);
-            n += *(volatile int32_t*)&ws->part_cnt[b]; nn |= *(volatile int32_t*)&ws->part_nan[b]; a += *(volatile int32_t*)&ws->part_add[b];
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            n += __shfl_xor_sync(0xffffffffu, n, o); nn |= __shfl_xor_sync(0xffffffffu, nn, o); a += __shfl_xor_sync(0xffffffffu, a, o);
-        }
-        __syncthreads();
-        if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0;
-        for (int w = 0; w < CW; ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; }
-        float out[4];
-        out[0] = (float)s + p.qd_offset * (float)n;               // qd_score   (metrics.py:92-93)
-        out[1] = nn ? NAN : m;                                     // max_fitness (:95)
-        out[2] = 100.0f * __fdiv_rn((float)n, (float)p.K);         // coverage   (:94)
-        out[3] = (float)a;                                         // offspring inserted by this call
-        if (tail) for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (p.metrics_out) p.metrics_out[j] = out[j]; }
-        ws->ticket = 0u;
-        ws->cta_arrived = 0u;
-        ws->job_count = 0u;
-        ws->commit_seq = seq;
-        if (mode == 2 && ws->xchg_nranks > 0) {                    // peer-memory exchange: next generation, other key table
-            uint32_t* ep = (uint32_t*)((char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET);
-            *ep = *ep + 1u;
+        if (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1) {
+            QDX_TRACE_MAX(6);                                     // end
+            ws->ticket = 0u;
+            ws->cta_arrived = 0u;
+            ws->job_count = 0u;
+            ws->job_next = 0u;
+            ws->commit_seq = seq;
+            if (mode == 2 && ws->xchg_nranks > 0) {                    // peer-memory exchange: next generation, other key table
+                uint32_t* ep = (uint32_t*)((char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET);
+                *ep = *ep + 1u;
+            }
         }
     }
 }
@@ -367,6 +479,18 @@ int qdx_launch_commit_generic(void* ws, int64_t K, int64_t D, int32_t desc_dim, 
                               float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
                               int32_t mode, cudaStream_t stream);      // qdx_mapelites.cu: warp-per-cell kernel, ordinary launch
 
+#if QDX_COMMIT_TRACE
+extern "C" int qdx_debug_commit_trace(unsigned long long* out8, int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out8) e = cudaMemcpyFromSymbol(out8, g_commit_trace, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) {
+        unsigned long long init[8] = {~0ull, ~0ull, 0ull, 0ull, ~0ull, 0ull, 0ull, 0ull};     // [7] = metrics written (service CTA)
+        e = cudaMemcpyToSymbol(g_commit_trace, init, sizeof(init));
+    }
+    return (int)e;
+}
+#endif
+
 extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
                           const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
                           float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
@@ -390,6 +514,11 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
     p.idx_base = idx_base; p.B = B; p.first_wins = first_wins; p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.rep_d = rep_desc;
     p.qd_offset = qd_offset; p.metrics_out = metrics_out4; p.added_cells = added_cells; p.mode = mode;
     void* args[] = {(void*)&p};
+#if defined(QDX_COMMIT_NOCOOP)      // timing experiment only: co-residency is NOT guaranteed by an ordinary launch
+    qdx_commit_stream_kernel<<<dim3((unsigned)(nblk + 1)), dim3(CW * 32), (size_t)CW * NST * CHUNK, (cudaStream_t)stream>>>(p);
+    (void)args;
+    return (int)cudaGetLastError();
+#endif
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)qdx_commit_stream_kernel, dim3((unsigned)(nblk + 1)), dim3(CW * 32), args,
                                                 (size_t)CW * NST * CHUNK, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : (int)e;

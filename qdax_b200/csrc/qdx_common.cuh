@@ -54,7 +54,7 @@ struct QdxWorkspace {
     uint32_t commit_seq;
     uint32_t cta_arrived;   // grid barrier of the streaming commit (reset by its last CTA)
     uint32_t job_count;     // entries of the global list of changed cells (reset by the last CTA)
-    uint32_t pad1;
+    uint32_t job_next;      // next batch of the list handed out to a streaming warp (reset by the last CTA)
 };
 
 __host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
