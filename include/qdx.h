@@ -189,6 +189,28 @@ int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, 
 int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,
                           float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval, float* out,
                           void* stream);
+/* ---- pytree genotypes.  An individual is stored as ONE packed row: the concatenation of its
+ * flattened leaves in jax.tree.leaves order, leaf l owning genes [off[l], off[l+1]).  isoline_variation on a pytree
+ * (mutation_operators.py:205-224) shares the line noise across leaves and draws leaf l's iso noise as
+ * normal(split(key', n_leaves)[l], (B,) + leaf_shape), i.e. with counter i * size_l + j inside the leaf. */
+#define QDX_MAX_LEAVES 32
+typedef struct qdx_leaf_table {
+    int32_t n;                          /* 1 .. QDX_MAX_LEAVES */
+    int32_t off[QDX_MAX_LEAVES + 1];    /* off[0] = 0 <= off[1] <= ... <= off[n] = D */
+    uint32_t key[2 * QDX_MAX_LEAVES];   /* key words of split(key', n)[l] */
+} qdx_leaf_table;
+/* MixingEmitter.emit (variation only) for a pytree genotype: two selections + isoline over packed rows; gen_keys8 as for
+ * qdx_generate (its leaf key is ignored, the table's keys are used). */
+int qdx_generate_leaves(const float* rep_genotypes, const float* rep_fitness, void* ws, int64_t K, int64_t D, int64_t B,
+                        float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
+                        float* out_genotypes, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8,
+                        const qdx_leaf_table* leaves, void* stream);
+/* isoline_variation(x1, x2, key) on dense packed parents; (line_k0, line_k1) = split(key)[1] */
+int qdx_isoline_variation_leaves(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t line_k0, uint32_t line_k1,
+                                 const qdx_leaf_table* leaves, float iso_sigma, float line_sigma, int32_t has_min, float minval,
+                                 int32_t has_max, float maxval, float* out, void* stream);
+/* strided 2-D float copy (rows x cols, leading dimensions in floats): packs / unpacks leaves into / out of packed rows */
+int qdx_copy_2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols, void* stream);
 /* polynomial_mutation (mutation_operators.py:81-117; n_mutate = int(proportion_to_mutate * D), eta_plus_1 = 1 + eta,
  * mutpow = 1 / (1 + eta)) and polynomial_crossover (:139-172; n_change = int(proportion_var_to_change * D)).
  * out must not alias the inputs. */

@@ -147,6 +147,34 @@ def isoline_variation(x1, x2, key, iso_sigma, line_sigma, minval=None, maxval=No
     return out
 
 
+def _offsets(leaf_sizes) -> np.ndarray:
+    return np.ascontiguousarray(np.concatenate([[0], np.cumsum(leaf_sizes)]), dtype=np.int32)
+
+
+def isoline_variation_leaves(x1, x2, key, leaf_sizes, iso_sigma, line_sigma, minval=None, maxval=None) -> np.ndarray:
+    """isoline_variation on a pytree genotype given as packed rows (B, sum(leaf_sizes)), leaves in jax.tree.leaves order."""
+    x1, x2 = _f(x1), _f(x2)
+    B, D = x1.shape
+    off = _offsets(leaf_sizes)
+    out = np.zeros((B, D), dtype=F32)
+    _chk(lib().qo_isoline_variation_leaves(_p(x1), _p(x2), C.c_int64(B), C.c_int64(D), _p(_key(key)), C.c_int(len(leaf_sizes)), _p(off),
+                                           C.c_float(iso_sigma), C.c_float(line_sigma), *_clip_args(minval, maxval), _p(out)), "isoline_leaves")
+    return out
+
+
+def emit_isoline_leaves(rep_g, rep_f, key, B, leaf_sizes, iso_sigma, line_sigma, minval=None, maxval=None):
+    rep_g, rep_f = _f(rep_g), _f(rep_f).reshape(-1)
+    K, D = rep_g.shape
+    off = _offsets(leaf_sizes)
+    out = np.zeros((B, D), dtype=F32)
+    p1 = np.zeros(B, dtype=np.int32)
+    p2 = np.zeros(B, dtype=np.int32)
+    _chk(lib().qo_emit_isoline_leaves(_p(rep_g), _p(rep_f), C.c_int64(K), C.c_int64(D), _p(_key(key)), C.c_int64(B), C.c_int(len(leaf_sizes)),
+                                      _p(off), C.c_float(iso_sigma), C.c_float(line_sigma), *_clip_args(minval, maxval),
+                                      _p(out), _p(p1), _p(p2)), "emit_leaves")
+    return out, p1, p2
+
+
 def emit_isoline(rep_g, rep_f, key, B, iso_sigma, line_sigma, minval=None, maxval=None):
     rep_g, rep_f = _f(rep_g), _f(rep_f).reshape(-1)
     K, D = rep_g.shape

@@ -231,6 +231,30 @@ def isoline_variation(x1, x2, key, iso_sigma, line_sigma, minval=None, maxval=No
     return x.astype(F32)
 
 
+def isoline_variation_tree(x1_leaves, x2_leaves, key, iso_sigma, line_sigma, minval=None, maxval=None):
+    """mutation_operators.py:175-226 on a pytree genotype given as its list of leaves (jax.tree.leaves order), each of
+    shape (B, ...): shared line noise (:205-207), keys = split(key, nb_leaves) (:220), one normal(key_l, leaf.shape) per
+    leaf (:210)."""
+    B = np.asarray(x1_leaves[0]).shape[0]
+    ks = jr.split(key)  # :205
+    key, k_line = ks[0], ks[1]
+    line = (jr.normal(k_line, (B,)) * F32(line_sigma)).astype(F32)  # :207
+    keys = jr.split(key, len(x1_leaves))  # :220
+    out = []
+    for a, b, k in zip(x1_leaves, x2_leaves, keys):
+        a = np.asarray(a, dtype=F32)
+        b = np.asarray(b, dtype=F32)
+        iso = (jr.normal(k, a.shape) * F32(iso_sigma)).astype(F32)  # :210
+        ln = line.reshape((B,) + (1,) * (a.ndim - 1))  # jax.vmap(jnp.multiply)((x2 - x1), line_noise)
+        x = ((a + iso).astype(F32) + ((b - a).astype(F32) * ln).astype(F32)).astype(F32)  # :211
+        if minval is not None:
+            x = np.maximum(x, F32(minval))
+        if maxval is not None:
+            x = np.minimum(x, F32(maxval))
+        out.append(x.astype(F32))
+    return out
+
+
 def _polynomial_mutation_row(x, key, proportion_to_mutate, eta, minval, maxval) -> np.ndarray:
     """mutation_operators.py:12-78 for one genotype."""
     x = np.asarray(x, dtype=F32).copy()

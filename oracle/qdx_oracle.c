@@ -288,6 +288,38 @@ QO_API int qo_select_indices(const float* fit, int64_t K, const uint32_t* key, i
  * qdax/core/emitters/mutation_operators.py:175-226 (single-leaf genotype).
  * x = (x1 + iso) + (x2 - x1) * line ; clip.  Parents given by index into a (K, D) table when
  * p1/p2 are non-NULL, else x1/x2 are dense (B, D). */
+/* Pytree genotypes (:219-224): an individual is the concatenation of its flattened leaves (jax.tree.leaves order), leaf l
+ * owning genes [off[l], off[l+1]) of the packed row; keys = split(key, nb_leaves); leaf l's noise is
+ * normal(keys[l], (B,) + leaf_shape), i.e. counter i * size_l + j.  n_leaves <= 1 / off == NULL: one leaf of D genes. */
+static void isoline_leaves(const float* x1, const float* x2, const int32_t* p1, const int32_t* p2, int64_t B, int64_t D,
+                           qo_key key, int n_leaves, const int32_t* off, float iso_sigma, float line_sigma, int has_min, float minv,
+                           int has_max, float maxv, float* out) {
+    qo_key k_line = split_i(key, 1);             /* :205  key, key_line_noise = split(key) */
+    qo_key k_rest = split_i(key, 0);
+    const int32_t one_off[2] = {0, (int32_t)D};
+    if (n_leaves <= 1 || !off) { n_leaves = 1; off = one_off; }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < B; ++i) {
+        float line = normal_from_bits(bits32(k_line, (uint64_t)i)) * line_sigma;   /* :207 */
+        const float* a = p1 ? x1 + (int64_t)p1[i] * D : x1 + i * D;
+        const float* b = p2 ? x2 + (int64_t)p2[i] * D : x2 + i * D;
+        for (int l = 0; l < n_leaves; ++l) {
+            const qo_key k_leaf = split_i(k_rest, (uint64_t)l);          /* :220  split(key, nb_leaves)[l] */
+            const int64_t sz = off[l + 1] - off[l];
+            for (int64_t j = 0; j < sz; ++j) {
+                const int64_t d = off[l] + j;
+                float iso = normal_from_bits(bits32(k_leaf, (uint64_t)(i * sz + j))) * iso_sigma;   /* :210 */
+                float t1 = a[d] + iso;
+                float t2 = b[d] - a[d];
+                float t3 = t2 * line;
+                float x = t1 + t3;                                                             /* :211 */
+                if (has_min) x = max_nanprop(x, minv);                                              /* :214-215 */
+                if (has_max) x = min_nanprop(x, maxv);
+                out[i * D + d] = x;
+            }
+        }
+    }
+}
 static void isoline(const float* x1, const float* x2, const int32_t* p1, const int32_t* p2, int64_t B, int64_t D,
                     qo_key key, float iso_sigma, float line_sigma, int has_min, float minv, int has_max, float maxv,
                     float* out) {
@@ -316,6 +348,14 @@ QO_API int qo_isoline_variation(const float* x1, const float* x2, int64_t B, int
                                 float* out) {
     qo_key k = {key[0], key[1]};
     isoline(x1, x2, NULL, NULL, B, D, k, iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
+    return 0;
+}
+QO_API int qo_isoline_variation_leaves(const float* x1, const float* x2, int64_t B, int64_t D, const uint32_t* key, int n_leaves,
+                                       const int32_t* off, float iso_sigma, float line_sigma, int has_min, float minv, int has_max,
+                                       float maxv, float* out) {
+    qo_key k = {key[0], key[1]};
+    if (n_leaves < 1 || !off || off[0] != 0 || off[n_leaves] != D) return -1;
+    isoline_leaves(x1, x2, NULL, NULL, B, D, k, n_leaves, off, iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
     return 0;
 }
 /* ------------------------------------------------------------------ polynomial mutation / crossover
@@ -422,6 +462,20 @@ QO_API int qo_emit_isoline(const float* rep_g, const float* rep_f, int64_t K, in
     rc = select_indices(rep_f, K, split_i(k, 1), B, p2);      /* :59 */
     if (rc) return rc;
     isoline(rep_g, rep_g, p1, p2, B, D, split_i(k, 2), iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
+    return 0;
+}
+
+/* the same for a pytree genotype stored as packed rows */
+QO_API int qo_emit_isoline_leaves(const float* rep_g, const float* rep_f, int64_t K, int64_t D, const uint32_t* key, int64_t B,
+                                  int n_leaves, const int32_t* off, float iso_sigma, float line_sigma, int has_min, float minv,
+                                  int has_max, float maxv, float* out, int32_t* p1, int32_t* p2) {
+    qo_key k = {key[0], key[1]};
+    if (n_leaves < 1 || !off || off[0] != 0 || off[n_leaves] != D) return -1;
+    int rc = select_indices(rep_f, K, split_i(k, 0), B, p1);
+    if (rc) return rc;
+    rc = select_indices(rep_f, K, split_i(k, 1), B, p2);
+    if (rc) return rc;
+    isoline_leaves(rep_g, rep_g, p1, p2, B, D, split_i(k, 2), n_leaves, off, iso_sigma, line_sigma, has_min, minv, has_max, maxv, out);
     return 0;
 }
 

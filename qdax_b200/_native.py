@@ -458,6 +458,28 @@ def isoline_variation(x1, x2, key, iso_sigma, line_sigma, minval=None, maxval=No
     return out
 
 
+def generate_leaves(rep_g, rep_f, ws: "Workspace", B: int, iso_sigma: float, line_sigma: float, minval, maxval, out_g, gen_keys,
+                    leaves, out_p1=None, out_p2=None) -> None:
+    """MixingEmitter.emit (variation only) for a pytree genotype stored as packed rows."""
+    K, D = rep_g.shape
+    call("qdx_generate_leaves", _ptr(rep_g), _ptr(rep_f), ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B), C.c_float(iso_sigma),
+         C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0), C.c_int32(maxval is not None),
+         C.c_float(maxval or 0.0), _ptr(out_g), _ptr(out_p1), _ptr(out_p2), gen_keys, C.byref(leaves), _stream())
+
+
+def isoline_variation_leaves(x1, x2, line_key, leaves, iso_sigma, line_sigma, minval=None, maxval=None) -> torch.Tensor:
+    """isoline_variation on packed (B, D_total) parents of a pytree genotype; line_key = split(key)[1]."""
+    x1 = require_cuda(x1, "x1")
+    x2 = require_cuda(x2, "x2")
+    B, D = x1.shape
+    k0, k1 = key_words(line_key)
+    out = torch.empty_like(x1)
+    call("qdx_isoline_variation_leaves", _ptr(x1), _ptr(x2), C.c_int64(B), C.c_int64(D), C.c_uint32(k0), C.c_uint32(k1), C.byref(leaves),
+         C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
+         C.c_int32(maxval is not None), C.c_float(maxval or 0.0), _ptr(out), _stream())
+    return out
+
+
 def polynomial_mutation(x, key, proportion_to_mutate: float, eta: float, minval: float, maxval: float) -> torch.Tensor:
     x = require_cuda(x, "x")
     B = x.shape[0]

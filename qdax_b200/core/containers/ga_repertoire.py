@@ -9,6 +9,7 @@ from typing import Any, Dict, Optional, Tuple
 import torch
 
 from qdax_b200 import _native
+from qdax_b200 import tree_util
 from qdax_b200.core.emitters.repertoire_selectors.selector import Selector
 from qdax_b200.core.containers.repertoire import Repertoire
 
@@ -31,9 +32,20 @@ class GARepertoire(Repertoire):
     def _tensor_fields(self):
         return {k: v for k, v in vars(self).items() if isinstance(v, torch.Tensor) and not k.startswith("_")}
 
+    def _packed_genotypes(self):
+        """(genotypes as (N, D_total) rows, TreeSpec or None).  A pytree genotype lives in one packed buffer whose
+        leaves `self.genotypes` exposes as views (qdax_b200/tree_util.py), so this is free."""
+        g = self.genotypes
+        if tree_util.is_tree(g):
+            return tree_util.pack(g)
+        return g.reshape(g.shape[0], -1), None
+
     def _gather(self, idx: torch.Tensor):
         """x[idx] for every array field (reference uniform_selector.py:57-60)."""
         updates = {name: _native.gather_rows(_native.require_cuda(t, name), idx) for name, t in self._tensor_fields().items()}
+        if tree_util.is_tree(self.genotypes):
+            flat, spec = self._packed_genotypes()
+            updates["genotypes"] = tree_util.unpack(_native.gather_rows(flat, idx), spec)
         updates["extra_scores"] = {k: v[idx.long()] for k, v in self.extra_scores.items()}
         new = self.replace(**updates)
         new._ws = None
@@ -42,7 +54,7 @@ class GARepertoire(Repertoire):
     # ---- reference surface ----------------------------------------------------------------------------
     @property
     def size(self) -> int:
-        return int(self.genotypes.shape[0])
+        return int(self.fitnesses.shape[0])
 
     def select(self, key, num_samples: int, selector: Optional[Selector] = None):
         if selector is None:

@@ -20,6 +20,7 @@ import torch
 
 from qdax_b200 import _native
 from qdax_b200 import random as qrandom
+from qdax_b200 import tree_util
 from qdax_b200.core.emitters.repertoire_selectors.selector import Selector
 from qdax_b200.core.containers.ga_repertoire import GARepertoire
 
@@ -98,7 +99,12 @@ class MapElitesRepertoire(GARepertoire):
         return _native.grid_of(self.centroids)
 
     def _clone_state(self) -> "MapElitesRepertoire":
-        new = self.replace(genotypes=self.genotypes.clone(), fitnesses=self.fitnesses.clone(), descriptors=self.descriptors.clone(),
+        if tree_util.is_tree(self.genotypes):
+            flat, spec = self._packed_genotypes()
+            genotypes = tree_util.unpack(flat.clone(), spec)
+        else:
+            genotypes = self.genotypes.clone()
+        new = self.replace(genotypes=genotypes, fitnesses=self.fitnesses.clone(), descriptors=self.descriptors.clone(),
                            extra_scores={k: v.clone() for k, v in self.extra_scores.items()})
         return new
 
@@ -120,16 +126,20 @@ class MapElitesRepertoire(GARepertoire):
         if batch_of_extra_scores is None:
             batch_of_extra_scores = {}
         extras = self.filter_extra_scores(batch_of_extra_scores)
-        g = _native.require_cuda(batch_of_genotypes, "batch_of_genotypes")
-        B = g.shape[0]
-        g2 = g.reshape(B, -1)
+        new = self if _donate else self._clone_state()
+        rep_g, spec = new._packed_genotypes()
+        if spec is not None:                      # pytree genotype: one packed row per individual (reference :234-240)
+            g2, _ = tree_util.pack(batch_of_genotypes, spec)
+            g = g2
+        else:
+            g = _native.require_cuda(batch_of_genotypes, "batch_of_genotypes")
+            g2 = g.reshape(g.shape[0], -1)
+        B = g2.shape[0]
         d = _native.require_cuda(batch_of_descriptors, "batch_of_descriptors")
         f = _native.require_cuda(batch_of_fitnesses, "batch_of_fitnesses").reshape(-1)
         if f.numel() != B or d.shape[0] != B:
             raise ValueError("batch size mismatch between genotypes, descriptors and fitnesses")
-        new = self if _donate else self._clone_state()
         K = new.centroids.shape[0]
-        rep_g = new.genotypes.reshape(K, -1)
         rep_f = new.fitnesses.reshape(-1)
         if rep_g.shape[1] != g2.shape[1]:
             raise ValueError("genotype dimension mismatch")
@@ -160,7 +170,8 @@ class MapElitesRepertoire(GARepertoire):
             extra_scores = {}
         extra_scores = {k: v for k, v in extra_scores.items() if k in keys_extra_scores}
         first_extra = {k: v[0] for k, v in extra_scores.items()}
-        rep = cls.init_default(genotype=genotypes[0], centroids=centroids, one_extra_score=first_extra,
+        first_genotype = tree_util.tree_map(lambda x: x[0], genotypes) if tree_util.is_tree(genotypes) else genotypes[0]   # :304
+        rep = cls.init_default(genotype=first_genotype, centroids=centroids, one_extra_score=first_extra,
                                keys_extra_scores=keys_extra_scores, tie_break=tie_break)
         return rep.add(genotypes, descriptors, fitnesses, extra_scores, _donate=True)
 
@@ -174,8 +185,13 @@ class MapElitesRepertoire(GARepertoire):
         one_extra_score = {k: v for k, v in one_extra_score.items() if k in keys_extra_scores}
         K = centroids.shape[0]
         dev = centroids.device
+        if tree_util.is_tree(genotype):           # :342-347: zeros_like every leaf with a leading K; here one packed buffer
+            spec = tree_util.spec_of(genotype, batched=False)
+            default_genotypes = tree_util.unpack(torch.zeros((K, spec.total), dtype=torch.float32, device=dev), spec)
+        else:
+            default_genotypes = torch.zeros((K,) + tuple(genotype.shape), dtype=torch.float32, device=dev)
         return cls(
-            genotypes=torch.zeros((K,) + tuple(genotype.shape), dtype=torch.float32, device=dev),
+            genotypes=default_genotypes,
             fitnesses=torch.full((K, 1), float("-inf"), dtype=torch.float32, device=dev),
             descriptors=torch.zeros_like(centroids),
             centroids=centroids,

@@ -15,6 +15,7 @@ import torch
 
 from qdax_b200 import _native
 from qdax_b200 import random as qrandom
+from qdax_b200 import tree_util
 from qdax_b200.core.containers.ga_repertoire import GARepertoire
 from qdax_b200.core.emitters.emitter import Emitter, EmitterState
 from qdax_b200.core.emitters.mutation_operators import isoline_variation
@@ -67,6 +68,19 @@ class MixingEmitter(Emitter):
                              gen_keys=_native.host_generation_keys(_native.KEYMODE_EMIT, key))
             return out, {}
 
+        if cfg is not None and tree_util.is_tree(g) and repertoire.fitnesses.shape[-1] == 1:
+            # pytree genotype: same fused select x2 + isoline over the packed rows, per-leaf noise keys (:219-224)
+            flat, spec = repertoire._packed_genotypes()
+            if spec.total % 4 == 0 and spec.n_leaves <= tree_util.MAX_LEAVES:
+                ws = repertoire._workspace()
+                _native.ensure_selection(repertoire.fitnesses.reshape(-1), ws)
+                kv = qrandom.split(key, 3)[2]                                            # :55
+                leaves = tree_util.leaf_table(spec, qrandom.split(qrandom.split(kv)[0], spec.n_leaves))    # mutation_operators.py:205, :220
+                out = torch.empty((self._batch_size, spec.total), dtype=torch.float32, device=flat.device)
+                _native.generate_leaves(flat, repertoire.fitnesses.reshape(-1), ws, self._batch_size, cfg["iso_sigma"], cfg["line_sigma"],
+                                        cfg["minval"], cfg["maxval"], out, _native.host_generation_keys(_native.KEYMODE_EMIT, key), leaves)
+                return tree_util.unpack(out, spec), {}
+
         n_variation = int(self._batch_size * self._variation_percentage)
         n_mutation = self._batch_size - n_variation
         if n_variation > 0:
@@ -83,7 +97,10 @@ class MixingEmitter(Emitter):
         elif n_mutation == 0:
             genotypes = x_variation
         else:
-            genotypes = torch.cat([x_variation, x_mutation], dim=0)                      # :75-80
+            if tree_util.is_tree(x_variation):                                           # :75-80
+                genotypes = tree_util.tree_map(lambda a, b: torch.cat([a, b], dim=0), x_variation, x_mutation)
+            else:
+                genotypes = torch.cat([x_variation, x_mutation], dim=0)
         return genotypes, {}
 
     @property

@@ -22,6 +22,22 @@ struct QdxGenKeys {
     QdxKey leaf;    // split(split(split(emit,3)[2])[0], 1)[0] -> iso noise
 };
 
+// Pytree genotypes: an individual is the concatenation of its leaves, leaf l owning genes
+// [off[l], off[l+1]) of the packed row; isoline_variation draws leaf l's noise from its own key with the counter
+// i * size_l + j (mutation_operators.py:219-224: keys = split(key, nb_leaves), normal(key_l, x1_l.shape)).
+#define QDX_MAX_LEAVES 32
+struct QdxLeafTab {
+    int32_t n;                              // 0 / 1 = single leaf (QdxGenKeys::leaf)
+    int32_t off[QDX_MAX_LEAVES + 1];
+    QdxKey key[QDX_MAX_LEAVES];
+};
+// leaf owning packed gene d (off[l] <= d < off[l+1]; empty leaves are skipped)
+QDX_DEV int qdx_leaf_of(const QdxLeafTab& lt, int32_t d) {
+    int lo = 0, hi = lt.n;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lt.off[mid] <= d) lo = mid; else hi = mid; }
+    return lo;
+}
+
 #define QDX_MAX_COMMIT_CTAS (148 * 8)
 #ifndef QDX_COMMIT_CTAS
 #define QDX_COMMIT_CTAS (148 * 8)      // grid cap of the commit kernel: measured better than one resident wave (148 * 4) for 4 KB rows (0.56 vs 0.42 of HBM peak)

@@ -203,6 +203,7 @@ struct QdxGenParams {
     int32_t offer; uint32_t idx_base; int32_t first_wins;
     int32_t keys_by_value; QdxGenKeys keys;          // generation keys derived on the host (qdx_host_generation_keys)
     QdxCvtIndex cvt;                                  // bucket index over non-grid centroids (GRID_DD < 0)
+    QdxLeafTab leaves;                                // pytree genotypes (MULTI instantiation only)
 };
 
 QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
@@ -214,12 +215,13 @@ constexpr int QDX_GEN_WARPS = 4;
 
 // ARM_CLIP: arm.py:27 clips the genotype to [0,1] before scoring; when the variation already clipped to a range
 // inside [0,1] that clip is the identity and is compiled out (bit-identical result).
-template <int TASK, int GRID_DD, bool ARM_CLIP>
+template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI>
 __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p);
 
-template <int TASK, int GRID_DD, bool ARM_CLIP>
+// MULTI: the packed row is the concatenation of several pytree leaves, each with its own noise key and counter space.
+template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI = false>
 __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(const QdxGenParams p) {
-    qdx_generate_body<TASK, GRID_DD, ARM_CLIP>(p);
+    qdx_generate_body<TASK, GRID_DD, ARM_CLIP, MULTI>(p);
     // multi-GPU peer-memory exchange: this CTA's offers (and their pushes into the peers) are done; the last CTA of
     // the grid publishes this rank's generation keys and raises its arrival flag in every peer
     if (GRID_DD != 0 && p.offer && p.keys_by_value) {
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
     }
 }
 
-template <int TASK, int GRID_DD, bool ARM_CLIP>
+template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI>
 __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
     extern __shared__ __align__(128) float s_tiles[];
     __shared__ QdxSeg s_seg[QDX_MAX_SEG];
@@ -300,8 +302,18 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
             for (int j = 0; j < 4; ++j) nz[j] = qdx_normal_from_bits_t<true>(qdx_bits32(keys.leaf, ctr + j));
 #else
             uint32_t bits[4];
+            if (MULTI) {                                    // per gene: the key and the counter space of its leaf
+                int l = qdx_leaf_of(p.leaves, d);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bits[j] = qdx_bits32(keys.leaf, ctr + j);     // four independent Threefry chains
+                for (int j = 0; j < 4; ++j) {
+                    while (l + 1 < p.leaves.n && d + j >= p.leaves.off[l + 1]) ++l;
+                    const int32_t o = p.leaves.off[l], sz = p.leaves.off[l + 1] - o;
+                    bits[j] = qdx_bits32(p.leaves.key[l], (uint64_t)(row0 + rr) * (uint64_t)sz + (uint64_t)(d + j - o));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bits[j] = qdx_bits32(keys.leaf, ctr + j);     // four independent Threefry chains
+            }
             qdx_normal4_from_bits(bits, nz);
 #endif
 #pragma unroll
@@ -946,6 +958,37 @@ __global__ void __launch_bounds__(256) qdx_isoline_kernel(const float* __restric
     out[e] = x;
 }
 
+// isoline_variation on dense parents of a pytree genotype, packed rows (mutation_operators.py:205-224): one shared line
+// noise per individual, leaf l's iso noise = normal(keys[l], (B, *leaf_shape)) -> counter i * size_l + j
+__global__ void __launch_bounds__(256) qdx_isoline_leaves_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                                 int64_t B, int32_t D, QdxKey k_line, const QdxLeafTab lt,
+                                                                 float iso_sigma, float line_sigma, int32_t has_min, float minv,
+                                                                 int32_t has_max, float maxv, float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * (int64_t)D) return;
+    const int64_t row = e / D;
+    const int32_t d = (int32_t)(e - row * D);
+    const int l = qdx_leaf_of(lt, d);
+    const int32_t o = lt.off[l], sz = lt.off[l + 1] - o;
+    const float line = qdx_normal_from_bits(qdx_bits32(k_line, (uint64_t)row)) * line_sigma;
+    const float iso = qdx_normal_from_bits(qdx_bits32(lt.key[l], (uint64_t)row * (uint64_t)sz + (uint64_t)(d - o))) * iso_sigma;
+    const float a = x1[e], b = x2[e];
+    float t1 = a + iso, t2 = b - a, t3 = t2 * line;
+    float x = t1 + t3;
+    if (has_min) x = qdx_max_nanprop(x, minv);
+    if (has_max) x = qdx_min_nanprop(x, maxv);
+    out[e] = x;
+}
+
+// strided 2-D copy: packs / unpacks the leaves of a pytree genotype into / out of the (N, D_total) row layout
+__global__ void __launch_bounds__(256) qdx_copy_2d_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
+                                                          int64_t dst_ld, int64_t rows, int64_t cols) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * cols) return;
+    const int64_t r = e / cols, c = e - r * cols;
+    dst[r * dst_ld + c] = src[r * src_ld + c];
+}
+
 // jax.random.{bits, uniform, normal, split} streams for the host-facing qdax_b200.random module
 __global__ void __launch_bounds__(256) qdx_random_kernel(QdxKey key, int64_t n, int32_t kind, float minv, float maxv, void* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1035,7 +1078,13 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, c
             default: return QDX_ERR_ARG;
         }
     } else if (TASK == QDX_TASK_NONE) {
-        QDX_LAUNCH_GEN(0);
+        if (p.leaves.n > 1) {
+            cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);
+        } else {
+            QDX_LAUNCH_GEN(0);
+        }
     } else {
         switch (gd) {
             case 0: QDX_LAUNCH_GEN(0); break;
@@ -1121,12 +1170,23 @@ int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t ke
     return 0;
 }
 
-int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
+static int fill_leaves(const qdx_leaf_table* in, int64_t D, QdxLeafTab* out) {
+    memset(out, 0, sizeof(*out));
+    if (!in) return 0;
+    if (in->n < 1 || in->n > QDX_MAX_LEAVES || in->off[0] != 0 || in->off[in->n] != D) return QDX_ERR_ARG;
+    for (int l = 0; l < in->n; ++l) if (in->off[l + 1] < in->off[l]) return QDX_ERR_ARG;
+    out->n = in->n;
+    for (int l = 0; l <= in->n; ++l) out->off[l] = in->off[l];
+    for (int l = 0; l < in->n; ++l) out->key[l] = QdxKey{in->key[2 * l], in->key[2 * l + 1]};
+    return 0;
+}
+
+static int generate_impl(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
                  int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, const qdx_cvt_index* cvt,
-                 void* stream) {
+                 const qdx_leaf_table* leaves, void* stream) {
     if (!rep_genotypes || !rep_fitness || !ws || K <= 0 || D <= 0 || B < 0 || (D & 3)) return QDX_ERR_ARG;
     if (task < QDX_TASK_NONE || task > QDX_TASK_SPHERE) return QDX_ERR_ARG;
     if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
@@ -1156,6 +1216,12 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
         p.keys_by_value = 1;
         p.keys.sel1 = QdxKey{gen_keys8[0], gen_keys8[1]}; p.keys.sel2 = QdxKey{gen_keys8[2], gen_keys8[3]};
         p.keys.line = QdxKey{gen_keys8[4], gen_keys8[5]}; p.keys.leaf = QdxKey{gen_keys8[6], gen_keys8[7]};
+    }
+    if (leaves) {
+        if (task != QDX_TASK_NONE || !gen_keys8) return QDX_ERR_ARG;
+        rc = fill_leaves(leaves, D, &p.leaves);
+        if (rc) return rc;
+        if (p.leaves.n == 1) p.keys.leaf = p.leaves.key[0];
     }
     const size_t smem = ((size_t)QDX_GEN_WARPS * 32 * p.DS + (size_t)p.grid.total_axes) * sizeof(float);
     const dim3 g((unsigned)((B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32)));
@@ -1320,6 +1386,51 @@ int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream) 
 }
 
 // jax.random.split(key, n): out[2 i .. 2 i + 1] = threefry(key, counter = (0, i))
+int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
+                 int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
+                 float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
+                 uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
+                 int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, const qdx_cvt_index* cvt,
+                 void* stream) {
+    return generate_impl(rep_genotypes, rep_fitness, centroids, ws, K, D, B, iso_sigma, line_sigma, has_min, minval, has_max, maxval,
+                         task, desc_dim, grid, offer, idx_base, first_wins, out_genotypes, out_fitness, out_desc, out_cells, out_p1,
+                         out_p2, gen_keys8, cvt, nullptr, stream);
+}
+
+int qdx_generate_leaves(const float* rep_genotypes, const float* rep_fitness, void* ws, int64_t K, int64_t D, int64_t B,
+                        float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval,
+                        float* out_genotypes, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8,
+                        const qdx_leaf_table* leaves, void* stream) {
+    if (!leaves || !gen_keys8) return QDX_ERR_ARG;
+    return generate_impl(rep_genotypes, rep_fitness, nullptr, ws, K, D, B, iso_sigma, line_sigma, has_min, minval, has_max, maxval,
+                         QDX_TASK_NONE, 1, nullptr, 0, 0u, 1, out_genotypes, nullptr, nullptr, nullptr, out_p1, out_p2, gen_keys8,
+                         nullptr, leaves, stream);
+}
+
+int qdx_isoline_variation_leaves(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t line_k0, uint32_t line_k1,
+                                 const qdx_leaf_table* leaves, float iso_sigma, float line_sigma, int32_t has_min, float minval,
+                                 int32_t has_max, float maxval, float* out, void* stream) {
+    if (!x1 || !x2 || !out || !leaves || B < 0 || D <= 0) return QDX_ERR_ARG;
+    QdxLeafTab lt;
+    int rc = fill_leaves(leaves, D, &lt);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    const int64_t n = B * D;
+    qdx_isoline_leaves_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(x1, x2, B, (int32_t)D, QdxKey{line_k0, line_k1}, lt,
+                                                                                iso_sigma, line_sigma, has_min, minval, has_max, maxval, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_copy_2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols, void* stream) {
+    if (!src || !dst || rows < 0 || cols < 0 || src_ld < cols || dst_ld < cols) return QDX_ERR_ARG;
+    if (rows == 0 || cols == 0) return 0;
+    const int64_t n = rows * cols;
+    qdx_copy_2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(src, src_ld, dst, dst_ld, rows, cols);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
 int qdx_host_split(uint32_t k0, uint32_t k1, int32_t n, uint32_t* out) {
     if (n < 0 || (n > 0 && !out)) return QDX_ERR_ARG;
     for (int32_t i = 0; i < n; ++i) h_threefry2x32(k0, k1, 0u, (uint32_t)i, &out[2 * i], &out[2 * i + 1]);
