@@ -189,6 +189,21 @@ int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, 
 int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,
                           float line_sigma, int32_t has_min, float minval, int32_t has_max, float maxval, float* out,
                           void* stream);
+/* ---- sibling insertion rules on the same cells + election + commit machinery.
+ * MELSRepertoire.add (qdax/core/containers/mels_repertoire.py:89-230): every individual comes with S evaluations.
+ * cells_all (B*S) = qdx_cells of all descriptors; per individual the kernel takes the most frequent cell (smallest on
+ * ties, _mode :51-57), the spread = mean pairwise descriptor distance (_dispersion :26-48; 0 when S == 1), the mean
+ * fitness (:169) and the centroid of the cell as stored descriptor (:162-164), writes them to out_*, and offers the
+ * individual to its cell iff fitness > rep_fitness[cell] && spread <= rep_spread[cell] (:181-187).  Collisions -- left
+ * to scatter order by the reference -- go to the first / last offspring index.  Follow with qdx_commit(out_genotypes =
+ * the batch, off_fitness = out_fitness, off_desc = out_desc, added_cells) and qdx_scatter_rows_by_source for the spreads. */
+int qdx_mels_offer(const int32_t* cells_all, const float* desc_all, const float* fit_all, int64_t B, int32_t S, int32_t desc_dim,
+                   const float* centroids, int64_t K, void* ws, const float* rep_fitness, const float* rep_spread,
+                   int32_t first_wins, int32_t* out_cells, float* out_fitness, float* out_spread, float* out_desc, void* stream);
+/* dst[c, :] = src[source_of_cell[c], :] where source_of_cell[c] >= 0 (qdx_commit's added_cells): per-cell side arrays
+ * (spreads, extra_scores; mapelites_repertoire.py:250-257) */
+int qdx_scatter_rows_by_source(const int32_t* source_of_cell, const float* src, int64_t K, int64_t W, float* dst, void* stream);
+
 /* ---- pytree genotypes.  An individual is stored as ONE packed row: the concatenation of its
  * flattened leaves in jax.tree.leaves order, leaf l owning genes [off[l], off[l+1]).  isoline_variation on a pytree
  * (mutation_operators.py:205-224) shares the line noise across leaves and draws leaf l's iso noise as

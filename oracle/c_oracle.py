@@ -218,6 +218,36 @@ def add(rep_g, rep_f, rep_d, g, f, desc, cell_idx, tie_break: str = "first"):
     return rep_g, rep_f, rep_d, sidx
 
 
+def mels_reduce(cells_all, desc_all, fit_all):
+    """(mode cell, spread, mean fitness) per individual from its S evaluations (mels_repertoire.py:26-57, :148-169)."""
+    fit_all = _f(fit_all)
+    B, S = fit_all.shape
+    desc_all = _f(desc_all).reshape(B, S, -1)
+    cells_all = np.ascontiguousarray(cells_all, dtype=np.int32).reshape(B, S)
+    cell = np.zeros(B, dtype=np.int32)
+    spread = np.zeros(B, dtype=F32)
+    fmean = np.zeros(B, dtype=F32)
+    _chk(lib().qo_mels_reduce(_p(cells_all), _p(desc_all), _p(fit_all), C.c_int64(B), C.c_int64(S), C.c_int64(desc_all.shape[2]),
+                              _p(cell), _p(spread), _p(fmean)), "mels_reduce")
+    return cell, spread, fmean
+
+
+def mels_add(rep_g, rep_f, rep_d, rep_spread, centroids, g, desc_all, fit_all, tie_break: str = "first"):
+    """MELSRepertoire.add (mels_repertoire.py:89-230) with the exact-arithmetic reduction; returns the new
+    (genotypes, fitnesses (K,), descriptors, spreads)."""
+    rep_g, rep_f, rep_d, rep_spread = _f(rep_g).copy(), _f(rep_f).reshape(-1).copy(), _f(rep_d).copy(), _f(rep_spread).copy()
+    centroids, g, fit_all = _f(centroids), _f(g), _f(fit_all)
+    B, S = fit_all.shape
+    cell, spread, fmean = mels_reduce(cells(_f(desc_all).reshape(B * S, -1), centroids), desc_all, fit_all)
+    cond = (fmean > rep_f[cell]) & (spread <= rep_spread[cell])
+    order = range(B - 1, -1, -1) if tie_break == "first" else range(B)
+    for b in order:
+        if cond[b]:
+            c = cell[b]
+            rep_g[c], rep_f[c], rep_d[c], rep_spread[c] = g[b], fmean[b], centroids[c], spread[b]
+    return rep_g, rep_f, rep_d, rep_spread
+
+
 def metrics(rep_f, qd_offset: float = 0.0) -> np.ndarray:
     rep_f = _f(rep_f).reshape(-1)
     out = np.zeros(3, dtype=F32)

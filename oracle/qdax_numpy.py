@@ -188,6 +188,51 @@ def repertoire_init(genotypes, fitnesses, descriptors, centroids, tie_break="fir
 # --------------------------------------------------------------------------------------
 # metrics -- qdax/utils/metrics.py:74-98
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------ MELS (qdax/core/containers/mels_repertoire.py)
+def mels_dispersion(descriptors: np.ndarray) -> np.float32:
+    """_dispersion :26-48: mean of the unique pairwise distances (float32; sums sequential, row-major over i < j)."""
+    d = np.asarray(descriptors, dtype=F32)
+    S = d.shape[0]
+    total = F32(0.0)
+    for i in range(S):
+        for j in range(i + 1, S):
+            diff = (d[i] - d[j]).astype(F32)
+            total = F32(total + F32(np.sqrt(seq_sum((diff * diff).astype(F32)[None, :])[0])))
+    return F32(total / F32(S * (S - 1) / 2.0))
+
+
+def mels_mode(x: np.ndarray) -> int:
+    """_mode :51-57: jnp.unique (sorted) + argmax of the counts (first maximum) = smallest most frequent value."""
+    vals, counts = np.unique(np.asarray(x), return_counts=True)
+    return int(vals[np.argmax(counts)])
+
+
+def mels_add(rep: "Repertoire", spreads: np.ndarray, genotypes, descriptors, fitnesses, tie_break: str = "first"):
+    """MELSRepertoire.add :89-230 on (B, S, Dd) descriptors and (B, S) fitnesses.  Returns (new repertoire, new spreads).
+    Every candidate with mean fitness > occupant and spread <= occupant's spread scatters to its cell; a collision is
+    resolved to the first / last offspring index (the reference leaves it to the scatter, :103-110)."""
+    g = np.asarray(genotypes, dtype=F32)
+    d = np.asarray(descriptors, dtype=F32)
+    f = np.asarray(fitnesses, dtype=F32)
+    B, S = f.shape
+    cells_all = get_cells_indices(d.reshape(B * S, -1), rep.centroids).reshape(B, S)  # :143-145
+    cell = np.array([mels_mode(cells_all[b]) for b in range(B)], dtype=np.int64)  # :148
+    spread = np.zeros(B, dtype=F32) if S == 1 else np.array([mels_dispersion(d[b]) for b in range(B)], dtype=F32)  # :152-158
+    fmean = (seq_sum(f) / F32(S)).astype(F32)  # :169
+    out = rep.copy()
+    new_spreads = np.array(spreads, dtype=F32, copy=True)
+    cond = (fmean > rep.fitnesses[cell, 0]) & (spread <= new_spreads[cell])  # :181-187
+    order = range(B - 1, -1, -1) if tie_break == "first" else range(B)  # the last write stays
+    for b in order:
+        if cond[b]:
+            c = cell[b]
+            out.genotypes[c] = g[b]
+            out.fitnesses[c, 0] = fmean[b]
+            out.descriptors[c] = rep.centroids[c]  # :162-164
+            new_spreads[c] = spread[b]
+    return out, new_spreads
+
+
 def default_qd_metrics(rep: Repertoire, qd_offset: float = 0.0) -> Dict[str, np.float32]:
     empty = rep.fitnesses == NEG_INF
     with np.errstate(invalid="ignore"):

@@ -479,6 +479,40 @@ QO_API int qo_emit_isoline_leaves(const float* rep_g, const float* rep_f, int64_
     return 0;
 }
 
+/* ------------------------------------------------------------------ MELS reduction
+ * qdax/core/containers/mels_repertoire.py: _mode :51-57 (smallest most frequent cell), _dispersion :26-48 (mean pairwise
+ * distance, 0 when S == 1 per :152-158), mean fitness :169.  Sums sequential, left to right. */
+QO_API int qo_mels_reduce(const int32_t* cells_all, const float* desc_all, const float* fit_all, int64_t B, int64_t S, int64_t Dd,
+                          int32_t* out_cell, float* out_spread, float* out_fmean) {
+    if (S < 1 || Dd < 1) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; ++b) {
+        const int32_t* c = cells_all + b * S;
+        int32_t mode = c[0]; int64_t best = 0;
+        for (int64_t i = 0; i < S; ++i) {
+            int64_t n = 0;
+            for (int64_t j = 0; j < S; ++j) n += (c[j] == c[i]);
+            if (n > best || (n == best && c[i] < mode)) { best = n; mode = c[i]; }
+        }
+        const float* d = desc_all + b * S * Dd;
+        float spread = 0.0f;
+        if (S > 1) {
+            float sum = 0.0f;
+            for (int64_t i = 0; i < S; ++i)
+                for (int64_t j = i + 1; j < S; ++j) {
+                    float acc = 0.0f;
+                    for (int64_t k = 0; k < Dd; ++k) { float t = d[i * Dd + k] - d[j * Dd + k]; acc = acc + t * t; }
+                    sum = sum + sqrtf(acc);
+                }
+            spread = sum / (float)((double)S * (double)(S - 1) / 2.0);
+        }
+        float fs = 0.0f;
+        for (int64_t i = 0; i < S; ++i) fs = fs + fit_all[b * S + i];
+        out_cell[b] = mode; out_spread[b] = spread; out_fmean[b] = fs / (float)S;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ scoring
  * task 0: arm (qdax/tasks/arm.py:9-38), 1: rastrigin, 2: sphere (qdax/tasks/standard_functions.py:9-24).
  * Descriptor of rastrigin/sphere = first Dd genes (Dd = 2 in the reference; other Dd is the declared
