@@ -348,10 +348,13 @@ def run_gpu(args, cfg):
                 "note": "ALU-bound kernel (one Threefry-2x32-20 block + erfinv per gene, sincos per joint): the HBM fraction is low by construction; see DESIGN.md section 6"}
     W = added_last
     commit_bytes = K * ab["commit_fixed_per_cell"] + W * ab["commit_per_winner"]
-    insert = {"kernel": "qdx_commit_kernel", "bound": "hbm", "achieved": commit_bytes / (kern_ms["commit"] * 1e-3) / 1e9, "peak": hbm_peak,
+    insert = {"kernel": "qdx_commit_stream_kernel", "bound": "hbm", "achieved": commit_bytes / (kern_ms["commit"] * 1e-3) / 1e9, "peak": hbm_peak,
               "unit": "GB/s", "frac": commit_bytes / (kern_ms["commit"] * 1e-3) / 1e9 / hbm_peak, "winners_last_step": W,
               "algorithmic_bytes_per_launch": commit_bytes, "avg_launch_ms": kern_ms["commit"],
               "note": "K=10^4: <= 8.4 MB per launch, launch/latency-bound (SURVEY.md 8d caveat)"}
+
+    if world == 1 and not args.no_insert_probe:
+        insert["large_rows"] = insert_probe(dev, hbm_peak)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -375,6 +378,66 @@ def run_gpu(args, cfg):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def insert_probe(dev, hbm_peak):
+    """The insert (commit) kernel where its HBM roofline is meaningful (SURVEY.md 8d caveat): BASELINE configs[3] shape --
+    K = 50 000 cells, D = 1000 (4 KB rows), Dd = 32 -- 65 536 offspring into an EMPTY repertoire, so ~30 000 winner rows
+    (~250 MB algorithmic) move in one launch.  Outside the timed region of the headline; CUDA events around ONE launch after
+    an L2-evicting read pass (median of 5), and around a train of 8 back-to-back launches into 8 empty repertoires."""
+    import numpy as np
+    import torch
+
+    from qdax_b200 import _native
+
+    K, D, Dd, B, R = 50000, 1000, 32, 65536, 8
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    cent = torch.rand(K, Dd, device=dev, generator=gen)
+    gs = [torch.rand(B, D, device=dev, generator=gen) for _ in range(2)]
+    d = torch.rand(B, Dd, device=dev, generator=gen)
+    f = torch.randn(B, device=dev, generator=gen)
+    cells = _native.cells(d, cent, None)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    m = torch.empty(4, device=dev)
+    new_rep = lambda: (torch.zeros(K, D, device=dev), torch.empty(K, device=dev), torch.zeros(K, Dd, device=dev), _native.Workspace(K, dev))
+    reps = [new_rep()]
+
+    def arm(n):
+        for (rg, rf, rd, w) in reps[:n]:
+            rf.fill_(float("-inf"))
+            _native.offer_cells(cells, f, w, rf)
+        flush.fill_(1)
+        _ = flush.view(torch.int32).sum()          # evict L2 with a READ pass: no dirty lines left to write back
+
+    single, train = [], []
+    for rep in range(6):
+        arm(1)
+        rg, rf, rd, w = reps[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _native.commit(w, gs[0], f, d, rg, rf, rd, metrics_out=m)
+        e1.record()
+        torch.cuda.synchronize()
+        single.append(e0.elapsed_time(e1))
+    W = float(m[3])
+    reps += [new_rep() for _ in range(R - 1)]
+    for rep in range(4):
+        arm(R)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r, (rg, rf, rd, w) in enumerate(reps):
+            _native.commit(w, gs[r & 1], f, d, rg, rf, rd, metrics_out=m)
+        e1.record()
+        torch.cuda.synchronize()
+        train.append(e0.elapsed_time(e1) / R)
+    nbytes = K * 20 + W * 2 * (4 * D + 4 * Dd + 4)
+    ms1, mst = float(np.median(single[1:])), float(np.median(train[1:]))
+    return {"workload": "K=50000 cells, D=1000, Dd=32, 65536 offspring into an empty repertoire (BASELINE configs[3] cold start)",
+            "winners": W, "algorithmic_bytes_per_launch": nbytes, "launch_ms": ms1, "achieved": nbytes / (ms1 * 1e-3) / 1e9,
+            "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (ms1 * 1e-3) / 1e9 / hbm_peak,
+            "train_of_8_launch_ms": mst, "train_of_8_frac": nbytes / (mst * 1e-3) / 1e9 / hbm_peak,
+            "timing": "CUDA events; single launch after an L2-evicting read pass (median of 5) / 8 back-to-back launches"}
 
 
 def cpu_baseline(cfg, args):
@@ -433,6 +496,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 16, help="offspring per generation in the CPU arm")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-insert-probe", action="store_true", help="skip the large-row insert-kernel measurement (N=1 only)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

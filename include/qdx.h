@@ -204,6 +204,17 @@ int qdx_mels_offer(const int32_t* cells_all, const float* desc_all, const float*
  * (spreads, extra_scores; mapelites_repertoire.py:250-257) */
 int qdx_scatter_rows_by_source(const int32_t* source_of_cell, const float* src, int64_t K, int64_t W, float* dst, void* stream);
 
+/* ---- compute_cvt_centroids on the GPU (mapelites_repertoire.py:30-72 calls scikit-learn KMeans on
+ * the host).  One Lloyd iteration = qdx_cells (assignment) + qdx_kmeans_accumulate + qdx_kmeans_update.  The update is
+ * order-free: coordinates (samples in [0, 1), as the reference clusters in the unit cube) are quantised to 32 fractional
+ * bits and summed with 64-bit integer atomics, centroid = (double)sum / count * 2^-32 -> float32, an empty cluster keeps its
+ * centroid.  acc (K * desc_dim), count (K) and changed (1) are zeroed by qdx_kmeans_accumulate; `changed` counts samples
+ * whose cell differs from prev_cells (NULL on the first iteration). */
+int qdx_kmeans_accumulate(const float* x, const int32_t* cells, const int32_t* prev_cells, int64_t N, int32_t desc_dim, int64_t K,
+                          unsigned long long* acc, int32_t* count, int32_t* changed, void* stream);
+int qdx_kmeans_update(const unsigned long long* acc, const int32_t* count, const float* old_centroids, int64_t K, int32_t desc_dim,
+                      float* new_centroids, void* stream);
+
 /* ---- pytree genotypes.  An individual is stored as ONE packed row: the concatenation of its
  * flattened leaves in jax.tree.leaves order, leaf l owning genes [off[l], off[l+1]).  isoline_variation on a pytree
  * (mutation_operators.py:205-224) shares the line noise across leaves and draws leaf l's iso noise as

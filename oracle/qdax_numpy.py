@@ -188,6 +188,32 @@ def repertoire_init(genotypes, fitnesses, descriptors, centroids, tie_break="fir
 # --------------------------------------------------------------------------------------
 # metrics -- qdax/utils/metrics.py:74-98
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------ CVT centroids by Lloyd iterations
+def lloyd_cvt_centroids(x: np.ndarray, num_centroids: int, num_iterations: int = 100):
+    """The GPU backend of compute_cvt_centroids (mapelites_repertoire.py:30-72 runs scikit-learn KMeans instead; this rule is
+    a declared replacement, see qdax_b200 lloyd_cvt_centroids): centroids start as the first K samples; assignment =
+    get_cells_indices (first minimum); update = per-cluster mean of the coordinates quantised to 32 fractional bits, summed
+    exactly in integers, (double)sum / count * 2^-32 -> float32; empty clusters keep their centroid; stop at a fixed point."""
+    x = np.asarray(x, dtype=F32)
+    N, Dd = x.shape
+    K = int(num_centroids)
+    cent = x[:K].copy()
+    q = np.minimum(np.floor(np.maximum(x, 0).astype(np.float64) * 4294967296.0), 4294967295.0).astype(np.uint64)
+    prev = None
+    it = 0
+    for it in range(1, num_iterations + 1):
+        cells = get_cells_indices(x, cent)
+        if prev is not None and np.array_equal(prev, cells):
+            break
+        acc = np.zeros((K, Dd), dtype=np.uint64)
+        np.add.at(acc, cells, q)
+        count = np.bincount(cells, minlength=K)
+        mean = ((acc.astype(np.float64) / np.maximum(count, 1)[:, None]) * (1.0 / 4294967296.0)).astype(F32)
+        cent = np.where((count > 0)[:, None], mean, cent).astype(F32)
+        prev = cells
+    return cent, it
+
+
 # ------------------------------------------------------------------ MELS (qdax/core/containers/mels_repertoire.py)
 def mels_dispersion(descriptors: np.ndarray) -> np.float32:
     """_dispersion :26-48: mean of the unique pairwise distances (float32; sums sequential, row-major over i < j)."""

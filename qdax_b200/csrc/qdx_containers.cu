@@ -1,6 +1,7 @@
 // Sibling insertion rules that reuse the cell assignment (c) and the packed-key election + streaming commit (d) of the
 // MAP-Elites path.  Reference files under /root/reference:
 //   MELSRepertoire.add          qdax/core/containers/mels_repertoire.py:89-230  (_dispersion :26-48, _mode :51-57)
+//   compute_cvt_centroids       qdax/core/containers/mapelites_repertoire.py:30-72   (Lloyd iterations on the GPU, rank 4)
 #include "qdx_common.cuh"
 #include "../../include/qdx.h"
 
@@ -72,7 +73,64 @@ __global__ void __launch_bounds__(256) qdx_scatter_by_source_kernel(const int32_
     if (i >= 0) dst[e] = src[(int64_t)i * W + w];
 }
 
+// ---- Lloyd iteration of compute_cvt_centroids (qdax/core/containers/mapelites_repertoire.py:30-72; the reference calls
+// scikit-learn's KMeans on the host).  Assignment = the cell-assignment kernels (c); the update below is ORDER-FREE and
+// therefore bit-reproducible: samples lie in [0, 1) (the reference clusters in the unit cube and rescales afterwards, :55-72),
+// each coordinate is quantised to 32 fractional bits and summed per (cluster, dimension) with 64-bit integer atomics; the new
+// centroid is (double)sum / count * 2^-32 rounded to float32; an empty cluster keeps its centroid.
+__global__ void __launch_bounds__(256) qdx_kmeans_accumulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ cells,
+                                                                    const int32_t* __restrict__ prev_cells, int64_t N, int32_t Dd, int64_t K,
+                                                                    unsigned long long* __restrict__ acc, int32_t* __restrict__ count,
+                                                                    int32_t* __restrict__ changed) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * Dd) return;
+    const int64_t i = e / Dd;
+    const int32_t d = (int32_t)(e - i * Dd);
+    const int32_t c = cells[i];
+    if (c < 0 || c >= K) return;
+    float v = x[e];
+    v = v < 0.0f ? 0.0f : v;                                           // also maps NaN to 0
+    double q = (double)v * 4294967296.0;
+    if (q > 4294967295.0) q = 4294967295.0;
+    atomicAdd(acc + (int64_t)c * Dd + d, (unsigned long long)q);
+    if (d == 0) {
+        atomicAdd(count + c, 1);
+        if (prev_cells && prev_cells[i] != c) atomicAdd(changed, 1);
+    }
+}
+__global__ void __launch_bounds__(256) qdx_kmeans_update_kernel(const unsigned long long* __restrict__ acc, const int32_t* __restrict__ count,
+                                                                const float* __restrict__ old_c, int64_t K, int32_t Dd, float* __restrict__ new_c) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * Dd) return;
+    const int32_t n = count[e / Dd];
+    new_c[e] = n > 0 ? (float)(((double)acc[e] / (double)n) * (1.0 / 4294967296.0)) : old_c[e];
+}
+
 }  // namespace
+
+extern "C" int qdx_kmeans_accumulate(const float* x, const int32_t* cells, const int32_t* prev_cells, int64_t N, int32_t desc_dim, int64_t K,
+                                     unsigned long long* acc, int32_t* count, int32_t* changed, void* stream) {
+    if (!x || !cells || !acc || !count || !changed || N < 0 || desc_dim < 1 || K <= 0) return QDX_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(unsigned long long) * (size_t)K * desc_dim, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)K, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(changed, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    if (N == 0) return 0;
+    const int64_t n = N * desc_dim;
+    qdx_kmeans_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, cells, prev_cells, N, desc_dim, K, acc, count, changed);
+    QDX_CHECK_LAUNCH_C();
+    return 0;
+}
+
+extern "C" int qdx_kmeans_update(const unsigned long long* acc, const int32_t* count, const float* old_centroids, int64_t K, int32_t desc_dim,
+                                 float* new_centroids, void* stream) {
+    if (!acc || !count || !old_centroids || !new_centroids || K <= 0 || desc_dim < 1) return QDX_ERR_ARG;
+    const int64_t n = K * desc_dim;
+    qdx_kmeans_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, count, old_centroids, K, desc_dim, new_centroids);
+    QDX_CHECK_LAUNCH_C();
+    return 0;
+}
 
 extern "C" int qdx_mels_offer(const int32_t* cells_all, const float* desc_all, const float* fit_all, int64_t B, int32_t S, int32_t desc_dim,
                               const float* centroids, int64_t K, void* ws, const float* rep_fitness, const float* rep_spread,
