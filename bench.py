@@ -291,24 +291,43 @@ def run_gpu(args, cfg):
     value = args.steps * B_total / (ms_total * 1e-3)
 
     # ---- e2e: the public API call a user makes, per step: host key in, metrics read back to the host ----------
+    # Two read-back disciplines, both inside the timed region: "pipelined" copies every step's metrics to PINNED host memory
+    # with an async D2H + event and consumes them one step behind (what a training loop that logs metrics does), so the host
+    # prepares step s+1 while step s runs; "blocking" calls .cpu() on the metrics after every step.
     e2e_steps = args.steps
     rep_e = rep
     hkey = key
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        ks = qr.split(hkey)                                   # host-side key chain, README.md:133
-        hkey, sub = ks[0], ks[1]
-        rep_e, state, md = me.update(rep_e, state, sub, donate=True)
-        host_metrics = me._last_metrics.cpu()                 # D2H of the step's metrics (16 B) + sync every step
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t[0])
+    pinned = torch.empty((2, 4), dtype=torch.float32).pin_memory()
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e = {}
+    for mode in ("blocking", "pipelined"):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s_i in range(e2e_steps):
+            ks = qr.split(hkey)                                   # host-side key chain, README.md:133
+            hkey, sub = ks[0], ks[1]
+            rep_e, state, md = me.update(rep_e, state, sub, donate=True)
+            if mode == "blocking":
+                host_metrics = me._last_metrics.cpu()             # D2H of the step's metrics (16 B) + sync every step
+            else:
+                pinned[s_i & 1].copy_(me._last_metrics, non_blocking=True)
+                evs[s_i & 1].record()
+                if s_i > 0:
+                    evs[(s_i - 1) & 1].synchronize()
+                    host_metrics = pinned[(s_i - 1) & 1].clone()  # step s-1's metrics, on the host, while step s runs
+        if mode == "pipelined":
+            evs[(e2e_steps - 1) & 1].synchronize()
+            host_metrics = pinned[(e2e_steps - 1) & 1].clone()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e[mode] = float(t[0])
+    e2e_ms = e2e["pipelined"]
     e2e_value = e2e_steps * B_total / (e2e_ms * 1e-3)
+    e2e_blocking_value = e2e_steps * B_total / (e2e["blocking"] * 1e-3)
 
     consistent = True
     if world > 1:
@@ -346,6 +365,10 @@ def run_gpu(args, cfg):
                 "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kern_ms[dom],
                 "note": "ALU-bound kernel (one Threefry-2x32-20 block + erfinv per gene, sincos per joint): the HBM fraction is low by construction; see DESIGN.md section 6"}
+    if dom == "generate" and args.config == "c3":
+        roofline["issue_bound_evidence"] = {"source": "profiles/r1_generate_v4_ncu_summary.txt (ncu --set full of this kernel at this config)",
+                                            "warp_instructions_per_offspring_row": 596.6, "issue_active_frac": 0.796, "alu_pipe_frac": 0.672,
+                                            "fma_pipe_frac": 0.405, "dram_frac": 0.066}
     W = added_last
     commit_bytes = K * ab["commit_fixed_per_cell"] + W * ab["commit_per_winner"]
     insert = {"kernel": "qdx_commit_stream_kernel", "bound": "hbm", "achieved": commit_bytes / (kern_ms["commit"] * 1e-3) / 1e9, "peak": hbm_peak,
@@ -365,8 +388,9 @@ def run_gpu(args, cfg):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": _config_dict(args, cfg, B_step=B_total),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "MAPElites.update(repertoire, emitter_state, key, donate=True) + metrics read back on the host every step"
-                       if world == 1 else "DistributedMAPElites.update(...) per rank + metrics read back every step",
+                "api": ("MAPElites.update(repertoire, emitter_state, key, donate=True)" if world == 1 else "DistributedMAPElites.update(...) per rank")
+                       + " + every step's metrics copied to pinned host memory (async D2H + event) and read one step behind",
+                "blocking_readback_value": e2e_blocking_value,
                 "note": "inputs of a step are the 2-word RNG key (host) and the HBM-resident repertoire (carried state)"},
         "gpu_launches": launches, "kernel_ms": kern_ms, "roofline": roofline, "insert_roofline": insert,
         "clocks": clocks, "replicas_bit_identical": consistent,
