@@ -641,9 +641,14 @@ def test_dns_golden_and_random(dev, golden, co):
     assert np.array_equal(N(out[0]), g["DNS_g"]) and np.array_equal(N(out[1]), g["DNS_f"], equal_nan=True)
     assert np.array_equal(N(out[2]), g["DNS_d"], equal_nan=True)
     rng = np.random.default_rng(5)
-    for P, B, D, Dd, k in [(1000, 300, 8, 2, 3), (513, 77, 4, 3, 5), (200, 64, 4, 6, 15), (4000, 1024, 12, 2, 1)]:
+    for P, B, D, Dd, k in [(1000, 300, 8, 2, 3), (513, 77, 4, 3, 5), (200, 64, 4, 6, 15), (4000, 1024, 12, 2, 1), (3000, 500, 4, 1, 2),
+                           (2500, 300, 4, 4, 4), (1500, 100, 4, 2, 20)]:
         pf = np.where(rng.random(P) < 0.9, np.round(rng.standard_normal(P), 1), -np.inf).astype(np.float32)
-        pd = np.where(np.isinf(pf)[:, None], np.nan, np.round(rng.random((P, Dd)), 2)).astype(np.float32)
+        if P == 2500:                                      # only on occupied slots (an empty slot carries a NaN descriptor)
+            occ = np.nonzero(np.isfinite(pf))[0]
+            pf[rng.choice(occ, 6, replace=False)] = np.nan  # NaN fitness: valid, never fitter, no fitter neighbours -> meta NaN
+            pf[rng.choice(np.nonzero(np.isfinite(pf))[0], 3, replace=False)] = np.inf
+        pd = np.where((pf == -np.inf)[:, None], np.nan, np.round(rng.random((P, Dd)), 2)).astype(np.float32)   # empty slots: NaN descriptor
         pg = rng.random((P, D)).astype(np.float32)
         bf = np.round(rng.standard_normal(B), 1).astype(np.float32)
         bd, bg = np.round(rng.random((B, Dd)), 2).astype(np.float32), rng.random((B, D)).astype(np.float32)
@@ -651,3 +656,9 @@ def test_dns_golden_and_random(dev, golden, co):
         out = _native.dns_add(T(pg, dev), T(pf, dev), T(pd, dev), T(bg, dev), T(bf, dev), T(bd, dev), k)
         assert np.array_equal(N(out[3]), meta, equal_nan=True) and np.array_equal(N(out[4]), surv)
         assert np.array_equal(N(out[0]), G) and np.array_equal(N(out[1]), F, equal_nan=True)
+    # degenerate ranking: every candidate identical (one bucket holds all keys; equal metas -> higher index first)
+    P, B = 700, 50
+    pg, bg = rng.random((P, 4)).astype(np.float32), rng.random((B, 4)).astype(np.float32)
+    G, F, Dn, meta, surv = co.dns_add(pg, np.ones(P, np.float32), np.full((P, 2), 0.5, np.float32), bg, np.ones(B, np.float32), np.full((B, 2), 0.5, np.float32), 3)
+    out = _native.dns_add(T(pg, dev), T(np.ones(P), dev), T(np.full((P, 2), 0.5), dev), T(bg, dev), T(np.ones(B), dev), T(np.full((B, 2), 0.5), dev), 3)
+    assert np.array_equal(N(out[3]), meta, equal_nan=True) and np.array_equal(N(out[4]), surv) and np.array_equal(N(out[0]), G)
