@@ -256,23 +256,37 @@ def run_gpu(args, cfg):
         key, m = step(rep, key)
     barrier()
 
-    # ---- timed region: K generations, device timed, per-kernel events recorded in the same region -------------
+    # ---- timed region: K generations, device timed (events around the whole region only).  The per-kernel timeline is
+    # taken in a second, instrumented pass of the same K steps right after it: an event record between two kernels stops the
+    # next launch from being staged behind the running one (~6 us per event, five per generation -- measured 0.411 vs
+    # 0.444 ms per generation at N = 2), so it must not sit inside the headline loop.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    me._timeline = []
     launches0 = _lib.launch_count
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         key, m = step(rep, key)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # CPU time to enqueue one generation (launch-only)
     ev1.record()
     barrier()
     launches = _lib.launch_count - launches0
-    tl, me._timeline = me._timeline, None
     ms_total = ev0.elapsed_time(ev1)
+    # instrumented pass: same loop with a CUDA event after every kernel (on the launching stream)
+    me._timeline = []
+    barrier()
+    iv0, iv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iv0.record()
+    for _ in range(args.steps):
+        key, m = step(rep, key)
+    iv1.record()
+    barrier()
+    tl, me._timeline = me._timeline, None
+    ms_instrumented = iv0.elapsed_time(iv1)
     clocks = sampler.stop() if rank == 0 else None
     per_kernel = {}
     prev = None
@@ -329,6 +343,13 @@ def run_gpu(args, cfg):
     e2e_value = e2e_steps * B_total / (e2e_ms * 1e-3)
     e2e_blocking_value = e2e_steps * B_total / (e2e["blocking"] * 1e-3)
 
+    if os.environ.get("QDX_TRACE") and hasattr(_lib.lib(), "qdx_debug_xchg_trace"):      # timing experiment builds only
+        import ctypes
+        t8 = (ctypes.c_ulonglong * 8)()
+        _lib.lib().qdx_debug_xchg_trace(t8, 0)
+        n_e, n_p = max(t8[0], 1), max(t8[3], 1)
+        sys.stderr.write("[xchg trace rank %d] elect launches %d: wait-for-flags %.2f us, elect kernel (CTA 0) %.2f us; publishes %d: %.2f us each\n"
+                         % (rank, t8[0], t8[1] / n_e / 1e3, t8[2] / n_e / 1e3, t8[3], t8[4] / n_p / 1e3))
     consistent = True
     if world > 1:
         from qdax_b200 import parallel
@@ -392,7 +413,10 @@ def run_gpu(args, cfg):
                        + " + every step's metrics copied to pinned host memory (async D2H + event) and read one step behind",
                 "blocking_readback_value": e2e_blocking_value,
                 "note": "inputs of a step are the 2-word RNG key (host) and the HBM-resident repertoire (carried state)"},
-        "gpu_launches": launches, "kernel_ms": kern_ms, "roofline": roofline, "insert_roofline": insert,
+        "gpu_launches": launches, "kernel_ms": kern_ms,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "kernel_ms_source": "instrumented pass of the same K steps right after the timed region (one CUDA event after every kernel); "
+                            "ms per step there: %.4f" % (ms_instrumented / args.steps), "roofline": roofline, "insert_roofline": insert,
         "clocks": clocks, "replicas_bit_identical": consistent,
         "exchange_used": (getattr(me, "_exchange", "none") if world > 1 else "none"), "exchange_fallback": getattr(me, "exchange_fallback", None),
         "final": {"coverage": coverage, "qd_score": qd, "inserted_last_step": added_last},

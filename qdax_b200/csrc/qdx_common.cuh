@@ -164,6 +164,16 @@ QDX_DEV void qdx_offer(void* ws_raw, int64_t K, const float* rep_f, int32_t c, f
     }
 }
 
+#ifndef QDX_XCHG_TRACE
+#define QDX_XCHG_TRACE 0      // timing experiments only: where a multi-GPU generation's tail goes (qdx_debug_xchg_trace)
+#endif
+#if QDX_XCHG_TRACE
+// [0] launches of the elect kernel, [1] sum ns waiting for the peers' flags, [2] sum ns elect kernel (CTA 0), [3] publishes,
+// [4] sum ns publish (keys + fence + flags to every peer)
+static __device__ unsigned long long g_xchg_trace[8];      // per translation unit; read from qdx_mapelites.cu
+QDX_DEV unsigned long long qdx_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 QDX_DEV void qdx_st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
@@ -198,6 +208,12 @@ QDX_DEV void qdx_xchg_cta_done(void* ws_raw, int64_t K, const QdxGenKeys& keys, 
     __threadfence();
     if (atomicAdd(&ws->push_ticket, 1u) == total_ctas - 1u) {
         ws->push_ticket = 0u;
+#if QDX_XCHG_TRACE
+        const unsigned long long t0 = qdx_now();
+#endif
         qdx_xchg_publish(ws, K, keys);
+#if QDX_XCHG_TRACE
+        atomicAdd(&g_xchg_trace[3], 1ull); atomicAdd(&g_xchg_trace[4], qdx_now() - t0);
+#endif
     }
 }

@@ -784,6 +784,9 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
     __shared__ float s_last[QDX_MAX_SEG];
     __shared__ float s_buf[8][3][128];
     QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+#if QDX_XCHG_TRACE
+    const unsigned long long tr_t0 = qdx_now();
+#endif
     if (wait_peers && threadIdx.x < ws->xchg_nranks) {     // acquire-spin on the LOCAL arrival flags (bounded: 2 s)
         const unsigned long long* flag = (const unsigned long long*)ws->xchg_peer[ws->xchg_rank] + threadIdx.x;
         const uint32_t want = *(const uint32_t*)((const char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET) + 1u;
@@ -797,6 +800,9 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
     const int nseg = ws->sel.nseg;
     for (int i = threadIdx.x; i < nseg; i += blockDim.x) { s_seg[i] = ws->sel.seg[i]; s_last[i] = ws->sel.last[i]; }
     __syncthreads();
+#if QDX_XCHG_TRACE
+    const unsigned long long tr_t1 = qdx_now();
+#endif
     if (nseg <= 0) return;
     const unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
     const int32_t* __restrict__ occ = qdx_ws_occ(ws_raw);
@@ -900,6 +906,11 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
         }
     }
     }
+#if QDX_XCHG_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&g_xchg_trace[0], 1ull); atomicAdd(&g_xchg_trace[1], tr_t1 - tr_t0); atomicAdd(&g_xchg_trace[2], qdx_now() - tr_t0);
+    }
+#endif
 }
 
 // =====================================================================================================
@@ -1120,6 +1131,15 @@ int qdx_launch_commit_generic(void* ws, int64_t K, int64_t D, int32_t desc_dim, 
     QDX_CHECK_LAUNCH();
     return 0;
 }
+
+#if QDX_XCHG_TRACE
+extern "C" int qdx_debug_xchg_trace(unsigned long long* out8, int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out8) e = cudaMemcpyFromSymbol(out8, g_xchg_trace, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) { unsigned long long z[8] = {0}; e = cudaMemcpyToSymbol(g_xchg_trace, z, sizeof(z)); }
+    return (int)e;
+}
+#endif
 
 extern "C" {
 
