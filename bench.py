@@ -57,7 +57,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -262,8 +262,9 @@ def run_gpu(args, cfg):
     # 0.444 ms per generation at N = 2), so it must not sit inside the headline loop.
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
+        sampler.start()                 # the recipe's clocks line (-lms 200): started before, killed after the timed region
+        time.sleep(0.7)                 # let nvidia-smi finish initialising: its first query stalls the GPU for ~0.5 ms, which
+                                        # is 15 % of a 4 ms timed region (20 generations at N = 8)
     launches0 = _lib.launch_count
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
