@@ -255,6 +255,15 @@ def run_gpu(args, cfg):
     for _ in range(max(args.warmup, 3)):
         key, m = step(rep, key)
     barrier()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for _ in range(5):                                        # rough ms per generation (after the one-time costs), untimed
+        key, m = step(rep, key)
+    w1.record()
+    barrier()
+    warm_ms = torch.tensor([w0.elapsed_time(w1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)        # the same figure, hence the same step count, on every rank
 
     # ---- timed region: K generations, device timed (events around the whole region only).  The per-kernel timeline is
     # taken in a second, instrumented pass of the same K steps right after it: an event record between two kernels stops the
@@ -263,8 +272,10 @@ def run_gpu(args, cfg):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                 # the recipe's clocks line (-lms 200): started before, killed after the timed region
-        time.sleep(0.7)                 # let nvidia-smi finish initialising: its first query stalls the GPU for ~0.5 ms, which
-                                        # is 15 % of a 4 ms timed region (20 generations at N = 8)
+    # nvidia-smi needs ~0.3 s to initialise and its first query stalls the GPU for ~0.5 ms -- 15 % of a 4 ms timed region (20
+    # generations at N = 8).  Keep the GPU under load with untimed generations (the same count on every rank) while it does.
+    for _ in range(min(int(600.0 / max(float(warm_ms[0]), 1e-3)) + 1, 20000)):
+        key, m = step(rep, key)
     launches0 = _lib.launch_count
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
