@@ -55,6 +55,10 @@ int qdx_workspace_keytab_offset(int64_t K, int64_t* offset);
 int qdx_workspace_init(void* ws, int64_t K, void* stream);
 int qdx_workspace_set_carry_key(void* ws, uint32_t k0, uint32_t k1, void* stream);
 /* blocking read-back of the scan carry key, last metrics {qd_score, max_fitness, coverage, num_added}, error flag */
+/* device-to-device copy of the scan carry key (two uint32 words) into (to_workspace != 0) or out of the workspace, stream
+ * ordered: lets a caller whose keys live on the device (jax.random.key_data under jit) drive the key_mode 2 chain of
+ * qdx_select_prepare without a host round trip (csrc/qdx_xla_ffi.cc) */
+int qdx_workspace_copy_carry_key(void* ws, uint32_t* key2_device, int32_t to_workspace, void* stream);
 int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream);
 
 /* ---- stage (a) set-up.  Replaces the p / cumsum part of UniformSelector.select

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "qdx_workspace_keytab_offset": [_i64, C.POINTER(_i64)],
     "qdx_workspace_init": [_vp, _i64, _vp],
     "qdx_workspace_set_carry_key": [_vp, _u32, _u32, _vp],
+    "qdx_workspace_copy_carry_key": [_vp, _vp, _i32, _vp],
     "qdx_workspace_read": [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_i32), _vp],
     "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
     "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],

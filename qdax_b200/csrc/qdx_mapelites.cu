@@ -1169,6 +1169,13 @@ int qdx_workspace_set_carry_key(void* ws, uint32_t k0, uint32_t k1, void* stream
     return (int)cudaMemcpyAsync((char*)ws + offsetof(QdxWorkspace, carry), k, sizeof(k), cudaMemcpyHostToDevice, S(stream));
 }
 
+int qdx_workspace_copy_carry_key(void* ws, uint32_t* key2_device, int32_t to_workspace, void* stream) {
+    if (!ws || !key2_device) return QDX_ERR_ARG;
+    char* carry = (char*)ws + offsetof(QdxWorkspace, carry);
+    return (int)(to_workspace ? cudaMemcpyAsync(carry, key2_device, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, S(stream))
+                              : cudaMemcpyAsync(key2_device, carry, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, S(stream)));
+}
+
 int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream) {
     if (!ws) return QDX_ERR_ARG;
     QdxWorkspace h;   // header only (a few KB)
