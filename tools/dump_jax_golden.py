@@ -56,6 +56,31 @@ def main(out):
     o["S_inj_cells"] = np.asarray(get_cells_indices(jnp.asarray(ref["S_inj_d"]), cent))
     new = rep.add(jnp.asarray(ref["S_emit_x"]), jnp.asarray(ref["S_inj_d"]), jnp.asarray(ref["S_inj_f"]))
     o["S_add_jax_g"], o["S_add_jax_f"], o["S_add_jax_d"] = np.asarray(new.genotypes), np.asarray(new.fitnesses).ravel(), np.asarray(new.descriptors)
+    # ---- rows added after round 1: pytree isoline, MELS, DNS -- inputs are generated here from fixed NumPy seeds, compare with
+    #      oracle/qdax_numpy.py (isoline_variation_tree, mels_add, dns_add) on the same inputs
+    from qdax.core.containers.dns_repertoire import DominatedNoveltyRepertoire
+    from qdax.core.containers.mels_repertoire import MELSRepertoire
+
+    rng = np.random.default_rng(0)
+    shapes = [(2, 3), (5,), (3, 2, 2)]
+    t1 = {f"leaf{i}": jnp.asarray(rng.random((23,) + s).astype(np.float32)) for i, s in enumerate(shapes)}
+    t2 = {f"leaf{i}": jnp.asarray(rng.random((23,) + s).astype(np.float32)) for i, s in enumerate(shapes)}
+    tv = isoline_variation(t1, t2, jax.random.key(3), iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0)
+    for i in range(len(shapes)):
+        o[f"T_x1_{i}"], o[f"T_x2_{i}"], o[f"T_out_{i}"] = np.asarray(t1[f"leaf{i}"]), np.asarray(t2[f"leaf{i}"]), np.asarray(tv[f"leaf{i}"])
+    cent6 = compute_euclidean_centroids((6, 6), 0.0, 1.0)
+    mels = MELSRepertoire.init_default(genotype=jnp.zeros(8), centroids=cent6)
+    mg = rng.random((64, 8)).astype(np.float32)
+    md = (rng.random((64, 1, 2)) + 0.15 * rng.standard_normal((64, 5, 2))).astype(np.float32)
+    mf = rng.standard_normal((64, 5)).astype(np.float32)
+    mels = mels.add(jnp.asarray(mg), jnp.asarray(md), jnp.asarray(mf))
+    o["M_g"], o["M_d"], o["M_f"] = mg, md, mf
+    o["M_out_g"], o["M_out_f"], o["M_out_d"], o["M_out_s"] = (np.asarray(mels.genotypes), np.asarray(mels.fitnesses).ravel(),
+                                                             np.asarray(mels.descriptors), np.asarray(mels.spreads))
+    dns = DominatedNoveltyRepertoire.init(genotypes=jnp.asarray(ref["DNS_pg"]), fitnesses=jnp.asarray(ref["DNS_pf"]).reshape(-1, 1),
+                                          descriptors=jnp.asarray(ref["DNS_pd"]), population_size=ref["DNS_pg"].shape[0], k=3)
+    dns = dns.add(jnp.asarray(ref["DNS_bg"]), jnp.asarray(ref["DNS_bd"]), jnp.asarray(ref["DNS_bf"]).reshape(-1, 1))
+    o["DNS_jax_g"], o["DNS_jax_f"], o["DNS_jax_d"] = np.asarray(dns.genotypes), np.asarray(dns.fitnesses).ravel(), np.asarray(dns.descriptors)
     np.savez_compressed(out, **o)
     print("wrote", out)
 
