@@ -51,6 +51,10 @@ constexpr int JB = QDX_COMMIT_JB;      // most list entries (changed cells) per 
 #ifndef QDX_COMMIT_CHUNK
 #define QDX_COMMIT_CHUNK 4096
 #endif
+#ifndef QDX_COMMIT_EARLY
+#define QDX_COMMIT_EARLY 0    // EXPERIMENT, not validated on a GPU yet (round 2): no grid barrier -- list entries are single 64-bit
+#endif                        // words, a warp that grabbed an index waits for that entry only, so CTAs that are done with phase 1
+                              // stream rows while late ones still scan their cells (phase 1 ends between 4 and 7 us after launch)
 #ifndef QDX_COMMIT_EXP
 #define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
 #endif
@@ -276,7 +280,12 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             unsigned base = 0;
             if (lane == 0 && wb) base = atomicAdd(&ws->job_count, (unsigned)__popc(wb));
             base = __shfl_sync(0xffffffffu, base, 0);
+#if QDX_COMMIT_EARLY
+            if (i >= 0) ((unsigned long long*)job_cell)[base + __popc(wb & ((1u << lane) - 1u))] =
+                            ((unsigned long long)(uint32_t)(c + 1) << 32) | (unsigned long long)(uint32_t)(i + 1);     // 0 = not yet written
+#else
             if (i >= 0) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
+#endif
         }
         // ---- this CTA's partial metrics and occupied count, published BEFORE the grid barrier: the service CTA sums them
         // while the rows stream
@@ -301,17 +310,101 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                 __threadfence();                              // ONE fence: partials + job list before the count and the arrival
                 if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
                 atomicAdd(&ws->cta_arrived, 1u);
+#if !QDX_COMMIT_EARLY
                 unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
                     unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
                 }
                 __threadfence();
+#endif
             }
         }
         __syncthreads();
         QDX_TRACE_MAX(3);                                     // last CTA through the grid barrier
 
+#if QDX_COMMIT_EARLY
+        // ---- phase 2 without a grid barrier: pairs of list indices from a grid-wide counter (one grab ahead); the warp
+        // waits for each entry to appear, or for "every CTA has arrived and the index is past the end of the list"
+        {
+            unsigned long long* jobs64 = (unsigned long long*)job_cell;
+            const uint32_t rowbytes = (uint32_t)p.D * 4u;
+            const bool bulk = (p.D & 3) == 0;
+            const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
+            unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
+            uint64_t* bars = &s_bar[wid * NST];
+            unsigned long long* sdst = &s_dst[wid * NST];
+            uint32_t* sby = &s_bytes[wid * NST];
+            uint32_t ql = 0, qs = 0;
+            constexpr unsigned JE = 2;
+            unsigned nb = 0;
+            if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+            bool done = QDX_COMMIT_EXP == 2;
+            while (!done) {
+                const unsigned cur = nb;
+                if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
+                for (unsigned e = 0; e < JE && !done; ++e) {
+                    const unsigned j = cur + e;
+                    unsigned long long ent = 0ull;
+                    if (lane == 0 && j < (unsigned)p.K) {
+                        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                        for (;;) {
+                            ent = *(volatile unsigned long long*)(jobs64 + j);
+                            if (ent) break;
+                            if (*(volatile unsigned*)&ws->cta_arrived >= (unsigned)nblk) {
+                                __threadfence();
+                                if (j >= *(volatile unsigned*)&ws->job_count) break;
+                            }
+                            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
+                        }
+                        if (ent) jobs64[j] = 0ull;                    // re-arm the slot for the next launch
+                    }
+                    ent = __shfl_sync(0xffffffffu, ent, 0);
+                    if (!ent) { done = true; break; }
+                    const int32_t cell = (int32_t)(uint32_t)(ent >> 32) - 1, src = (int32_t)(uint32_t)ent - 1;
+                    if (bulk) {
+                        if (lane == 0) {
+                            for (int pc = 0; pc < pieces; ++pc) {
+                                if (ql - qs >= (uint32_t)LEAD) {
+                                    const uint32_t sl = qs % NST;
+                                    mbar_wait(&bars[sl], (qs / NST) & 1u);
+                                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                    if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
+                                    ++qs;
+                                }
+                                const uint32_t sl = ql % NST;
+                                const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
+                                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");
+                                sdst[sl] = (unsigned long long)((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK);
+                                sby[sl] = bytes;
+                                mbar_expect_tx(&bars[sl], bytes);
+                                bulk_g2s(my_stage + sl * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes, &bars[sl]);
+                                ++ql;
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
+                        for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
+                    }
+                }
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+            }
+            if (bulk && lane == 0) {
+                while (qs < ql) {
+                    const uint32_t sl = qs % NST;
+                    mbar_wait(&bars[sl], (qs / NST) & 1u);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
+                    ++qs;
+                }
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+        }
+#else
         // ---- phase 2: the row copies, dealt out in batches of list entries.  SMs differ in their distance to the memory
         // they read and write, so a static deal leaves the slow ones streaming long after the fast ones are done (measured:
         // first CTA done at 36 us, last at 49 us).  Guided self-scheduling instead: warp g of the grid starts on batch g
@@ -396,6 +489,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         __syncwarp();
+#endif
         QDX_TRACE_MIN(4); QDX_TRACE_MAX(5);                   // first / last CTA done streaming
         // ---- my slice of the ordered occupied-cell list: offset = sum of the predecessors' counts (all published before
         // the grid barrier, so this is one batched read; doing it before the barrier instead was measured 6-8 us slower --
