@@ -10,7 +10,7 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 
 from oracle import qdax_numpy as qn  # noqa: E402
 
-SET = settings(max_examples=120, deadline=None)
+SET = settings(max_examples=120, deadline=None, derandomize=True, database=None)      # the same examples on every run
 SPECIAL = np.array([np.nan, -np.inf, np.inf, 0.0, -0.0], dtype=np.float32)
 
 
@@ -107,3 +107,35 @@ def test_mels_reduction_both_oracles_agree(co, seed, B, S, K_side):
     else:
         assert (spread == 0).all()
     assert np.allclose(fmean, qn.seq_sum(f) / np.float32(S), rtol=1e-7)
+
+
+@settings(max_examples=25, deadline=None, derandomize=True, database=None)
+@given(seed=st.integers(0, 10**6), R=st.sampled_from([1, 2, 4]), B_dev=st.integers(1, 96), task=st.sampled_from(["arm", "rastrigin", "sphere"]))
+def test_distributed_update_is_emit_per_rank_plus_one_replicated_add(co, seed, R, B_dev, task):
+    """DistributedMAPElites.update (distributed_map_elites.py:124-146): every rank emits from its own key (k, e = split(key);
+    emit(e)), the all_gather concatenates in rank order (global index = rank * B_dev + i) and ONE add runs on the concatenation --
+    both in the C oracle's fused routine and when spelled out with its single-rank pieces, and in the NumPy oracle."""
+    from oracle import jax_prng as jr
+
+    rng = np.random.default_rng(seed)
+    D = 8
+    cent = qn.compute_euclidean_centroids((5, 5), 0.0, 1.0)
+    init = rng.random((20, D)).astype(np.float32)
+    f0, d0 = co.score(task, init)
+    K = cent.shape[0]
+    g, f, d, _ = co.add(np.zeros((K, D)), np.full(K, -np.inf), np.zeros((K, 2)), init, f0, d0, co.cells(d0, cent))
+    keys = jr.split(jr.key(seed), R)
+    G, F, Dn, og, of, od, oc = co.distributed_update(g, f, d, cent, keys, B_dev, task)
+    xs = [co.emit_isoline(g, f, jr.split(keys[r])[1], B_dev, 0.05, 0.1, 0.0, 1.0)[0] for r in range(R)]
+    x = np.concatenate(xs, axis=0)
+    assert np.array_equal(og, x)
+    fx, dx = co.score(task, x)
+    assert np.array_equal(of, fx) and np.array_equal(od, dx) and np.array_equal(oc, co.cells(dx, cent))
+    G2, F2, D2, _ = co.add(g, f, d, x, fx, dx, oc)
+    assert np.array_equal(G, G2) and np.array_equal(F, F2) and np.array_equal(Dn, D2)
+    rep = qn.Repertoire(g.copy(), f.reshape(-1, 1).copy(), d.copy(), cent)
+    cfg = qn.EmitterConfig(batch_size=B_dev, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0)
+    new = qn.distributed_update(rep, list(keys), cfg, task)
+    new = new[0] if isinstance(new, tuple) else new
+    assert np.array_equal(np.isinf(new.fitnesses.ravel()), np.isinf(F))
+    assert np.allclose(new.genotypes, G, rtol=1e-5, atol=1e-6) and np.allclose(new.fitnesses.ravel(), F, rtol=1e-5, atol=1e-6)
