@@ -220,3 +220,37 @@ def test_jax_ffi_layer_is_gated_not_faked():
     if not have_jax:
         with pytest.raises(ImportError, match="jax"):
             importlib.import_module("qdax_b200.jax_ffi")
+
+
+def test_multi_sample_scoring_and_mels_driver_wiring():
+    """qdax/utils/sampling.py:111-152 and qdax/core/mels.py:33-60: sample s is scored with split(key, num_samples)[s], results are
+    stacked on axis 1, and MELS is MAPElites with that wrapper on a MELSRepertoire (CPU tensors: no kernel is involved here)."""
+    import functools
+
+    import torch
+
+    from qdax_b200 import random as qr
+    from qdax_b200.core.containers.mels_repertoire import MELSRepertoire
+    from qdax_b200.core.mels import MELS
+    from qdax_b200.utils.sampling import multi_sample_scoring_function
+
+    seen = []
+
+    def scoring(x, key):
+        seen.append(tuple(int(w) for w in key))
+        noise = float(int(key[1]) % 7)
+        return x.sum(dim=1) + noise, torch.stack([x[:, 0] + noise, x[:, 1]], dim=1), {"aux": x[:, :1] * noise, "tag": "t"}
+
+    x = torch.arange(12, dtype=torch.float32).reshape(4, 3)
+    key = qr.key(5)
+    f, d, extra = multi_sample_scoring_function(x, key, scoring, 3)
+    assert f.shape == (4, 3) and d.shape == (4, 3, 2) and extra["aux"].shape == (4, 3, 1) and extra["tag"] == ["t"] * 3
+    assert seen == [tuple(int(w) for w in k) for k in jr.split(jr.key(5), 3)]
+    for s in range(3):
+        fs, ds, _ = scoring(x, jr.split(jr.key(5), 3)[s])
+        assert torch.equal(f[:, s], fs) and torch.equal(d[:, s], ds)
+    me = MELS(scoring, emitter=None, metrics_function=lambda r: {}, num_samples=3)
+    assert isinstance(me._scoring_function, functools.partial) and me._scoring_function.keywords["num_samples"] == 3
+    assert me._repertoire_init.__func__ is MELSRepertoire.init.__func__ and me._num_samples == 3
+    f2, d2, _ = me._scoring_function(x, key)
+    assert torch.equal(f2, f) and torch.equal(d2, d)
