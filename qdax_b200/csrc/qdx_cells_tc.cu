@@ -54,7 +54,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef QDX_TC_WAIT_HINT
+#define QDX_TC_WAIT_HINT 0    // EXPERIMENT for round 2 (compiled, not yet run): suspend-time hint in ns for the mbarrier waits -- a third
+#endif                        // of the issued instructions of the v3 kernel are try_wait spins of the copy / MMA warps (r1_notes.md)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if QDX_TC_WAIT_HINT
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)QDX_TC_WAIT_HINT) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
@@ -63,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 // ---- bulk async copy global -> shared, completion on an mbarrier ----------------------------------------------
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
