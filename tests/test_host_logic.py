@@ -254,3 +254,13 @@ def test_multi_sample_scoring_and_mels_driver_wiring():
     assert me._repertoire_init.__func__ is MELSRepertoire.init.__func__ and me._num_samples == 3
     f2, d2, _ = me._scoring_function(x, key)
     assert torch.equal(f2, f) and torch.equal(d2, d)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/qdx.h must compile as C99 and as C++ on its own (no torch / CUDA types)."""
+    hdr = os.path.join(ROOT, "include", "qdx.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], ["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    assert "torch" not in text.lower().replace("no torch", "") and "#include <cuda" not in text
