@@ -25,7 +25,7 @@ extern "C" {
 #define QDX_ERR_EMPTY_REPERTOIRE (-3)  /* selection from an all-empty repertoire (p = 0/0 in the reference) */
 #define QDX_ERR_BAD_CELL (-4)          /* cell index out of range handed to qdx_offer_cells */
 #define QDX_ERR_BAD_INDEX (-5)         /* winner index outside the offspring buffer handed to qdx_commit */
-#define QDX_ERR_PEER_TIMEOUT (-6)      /* a peer's keys did not arrive within 2 s (peer-memory exchange) */
+#define QDX_ERR_PEER_TIMEOUT (-6)      /* a peer's keys did not arrive within the caller's time limit (peer-memory exchange) */
 #define QDX_ERR_INTERNAL (-7)          /* an in-kernel wait between CTAs timed out (never expected; reported instead of hanging) */
 
 /* task ids of the fused scoring functions */
@@ -60,6 +60,11 @@ int qdx_workspace_set_carry_key(void* ws, uint32_t k0, uint32_t k1, void* stream
  * qdx_select_prepare without a host round trip (csrc/qdx_xla_ffi.cc) */
 int qdx_workspace_copy_carry_key(void* ws, uint32_t* key2_device, int32_t to_workspace, void* stream);
 int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream);
+/* Host mirror of the sticky device error flag: `host_pinned` points at one int32 in pinned (page-locked, UVA) host memory,
+ * initialised to 0 by the caller.  Whichever kernel raises the flag (QDX_ERR_EMPTY_REPERTOIRE, _BAD_CELL, _BAD_INDEX,
+ * _PEER_TIMEOUT, _INTERNAL) also stores the code there, so the host can poll it between calls without a blocking
+ * read-back and without a copy on the stream.  NULL detaches. */
+int qdx_workspace_set_error_mirror(void* ws, int32_t* host_pinned, void* stream);
 
 /* ---- stage (a) set-up.  Replaces the p / cumsum part of UniformSelector.select
  * (repertoire_selectors/uniform_selector.py:43-45) and the jax.random.split chain of
@@ -159,8 +164,10 @@ int qdx_regenerate_winners(void* ws, int64_t K, int64_t D, int64_t B_dev, int32_
                            int32_t first_wins, float* stage_genotypes, void* stream);
 
 /* Same, fused with the scoring of the regenerated rows (stage_fitness (K,), stage_desc (K, desc_dim) are written for
- * the elected cells only), one warp per elected cell.  wait_peers != 0: first acquire-spin until every rank's keys of
- * this generation have arrived in the local exchange buffer (peer-memory exchange below; bounded, QDX_ERR_PEER_TIMEOUT). */
+ * the elected cells only), one warp per elected cell.  wait_peers > 0: first acquire-spin until every rank's keys of
+ * this generation have arrived in the local exchange buffer (peer-memory exchange below), for at most wait_peers
+ * MILLISECONDS: on timeout QDX_ERR_PEER_TIMEOUT is raised (device flag + host mirror), nothing is elected, and the
+ * qdx_commit(mode 2) that follows applies nothing and keeps the epoch -- replicas never diverge silently. */
 int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc_dim, int64_t B_dev, int32_t nranks,
                       const float* rep_genotypes, float iso_sigma, float line_sigma, int32_t has_min, float minval,
                       int32_t has_max, float maxval, int32_t first_wins, float* stage_genotypes, float* stage_fitness,
@@ -184,6 +191,42 @@ int qdx_xchg_close(void* peer_buf);
 int qdx_xchg_destroy(void* buf);
 int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, void* stream);
 int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream);
+
+/* ---- one whole generation per call: the body of MAPElites.update (qdax/core/map_elites.py:148-195) and, with
+ * nranks > 1, of DistributedMAPElites.update (qdax/core/distributed_map_elites.py:92-161) for the fused configuration
+ * (MixingEmitter with isoline variation only + arm / rastrigin / sphere scoring + default_qd_metrics).  Enqueues, in this
+ * order and on `stream`: the jax.random.split chain on the host (qdx_host_generation_keys with key_mode / (k0, k1) /
+ * carry_io2), qdx_generate (+ the offer when `grid` or `cvt` describes the tessellation), otherwise qdx_cells_tc (tc_prep
+ * and tc_scratch given) or qdx_cells with the offer, then qdx_commit -- or, with nranks > 1 (exchange must be
+ * QDX_EXCHANGE_P2P, the workspace attached with qdx_xchg_attach): [qdx_xchg_push ->] qdx_elect_winners(wait_peers = 1) ->
+ * qdx_commit(mode 2) through the per-cell staging rows.  Rank r's offspring have global indices [r * B, (r + 1) * B).
+ * The selection tables of the workspace must describe rep_fitness (qdx_select_prepare once, every qdx_commit afterwards).
+ * metrics_out4 (device, optional): {qd_score, max_fitness, coverage, offspring inserted}.  Non-blocking. */
+#define QDX_EXCHANGE_NONE 0
+#define QDX_EXCHANGE_P2P 1
+typedef struct qdx_step_desc {
+    float* rep_genotypes;     /* (K, D)  in place */
+    float* rep_fitness;       /* (K,)    in place, -inf = empty cell */
+    float* rep_desc;          /* (K, desc_dim) in place */
+    const float* centroids;   /* (K, desc_dim) */
+    void* ws;                 /* qdx_workspace_* */
+    int64_t K, D, B;          /* cells, genotype dimension, offspring of THIS rank per generation */
+    int32_t desc_dim, task;   /* QDX_TASK_ID_* */
+    float iso_sigma, line_sigma;
+    int32_t has_min; float minval;
+    int32_t has_max; float maxval;
+    const qdx_grid_desc* grid;          /* grid fast path, or NULL */
+    const struct qdx_cvt_index* cvt;    /* bucket index (desc_dim <= 3), or NULL */
+    const float* tc_prep;               /* qdx_cells_tc_prepare buffer (8 <= desc_dim <= 32), or NULL */
+    int32_t* tc_scratch;                /* qdx_cells_tc_workspace scratch_ints */
+    int32_t first_wins; float qd_offset;
+    float* off_genotypes; float* off_fitness; float* off_desc; int32_t* off_cells;   /* offspring buffers (B rows) */
+    int32_t rank, nranks, exchange;     /* 0, 1, QDX_EXCHANGE_NONE on one GPU */
+    int32_t peer_timeout_ms;            /* nranks > 1: how long qdx_elect_winners waits for the peers (<= 0: 30 000) */
+    float* stage_genotypes; float* stage_fitness; float* stage_desc;               /* per-cell staging rows (K), nranks > 1 */
+} qdx_step_desc;
+int qdx_map_elites_step(const qdx_step_desc* step, int32_t key_mode, uint32_t k0, uint32_t k1, uint32_t* carry_io2,
+                        float* metrics_out4, void* stream);
 
 /* ---- pieces of the preserved Python surface ---- */
 /* UniformSelector.select index stream for the key handed to select() (uniform_selector.py:48-55) */

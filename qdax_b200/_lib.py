@@ -69,6 +69,25 @@ class LeafTable(C.Structure):
 
 _i32, _i64, _u32, _f32, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_void_p
 
+
+class StepDesc(C.Structure):
+    """qdx_step_desc (include/qdx.h): everything one generation needs, filled once per (repertoire buffers, configuration)."""
+
+    _fields_ = [
+        ("rep_genotypes", _vp), ("rep_fitness", _vp), ("rep_desc", _vp), ("centroids", _vp), ("ws", _vp),
+        ("K", _i64), ("D", _i64), ("B", _i64),
+        ("desc_dim", _i32), ("task", _i32),
+        ("iso_sigma", _f32), ("line_sigma", _f32),
+        ("has_min", _i32), ("minval", _f32), ("has_max", _i32), ("maxval", _f32),
+        ("grid", C.POINTER(GridDesc)), ("cvt", C.POINTER(CvtIndexDesc)),
+        ("tc_prep", _vp), ("tc_scratch", _vp),
+        ("first_wins", _i32), ("qd_offset", _f32),
+        ("off_genotypes", _vp), ("off_fitness", _vp), ("off_desc", _vp), ("off_cells", _vp),
+        ("rank", _i32), ("nranks", _i32), ("exchange", _i32), ("peer_timeout_ms", _i32),
+        ("stage_genotypes", _vp), ("stage_fitness", _vp), ("stage_desc", _vp),
+    ]
+
+
 # name -> argtypes, exactly the prototypes of include/qdx.h
 PROTOTYPES = {
     "qdx_version": [],
@@ -77,6 +96,7 @@ PROTOTYPES = {
     "qdx_workspace_init": [_vp, _i64, _vp],
     "qdx_workspace_set_carry_key": [_vp, _u32, _u32, _vp],
     "qdx_workspace_copy_carry_key": [_vp, _vp, _i32, _vp],
+    "qdx_workspace_set_error_mirror": [_vp, _vp, _vp],
     "qdx_workspace_read": [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_i32), _vp],
     "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
     "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],
@@ -91,6 +111,7 @@ PROTOTYPES = {
     "qdx_xchg_destroy": [_vp],
     "qdx_xchg_attach": [_vp, _i32, _i32, C.POINTER(_vp), _vp],
     "qdx_xchg_push": [_vp, _i64, C.POINTER(_u32), _vp],
+    "qdx_map_elites_step": [C.POINTER(StepDesc), _i32, _u32, _u32, C.POINTER(_u32), _vp, _vp],
     "qdx_host_split": [_u32, _u32, _i32, _vp],
     "qdx_host_generation_keys": [_i32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)],
     "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],

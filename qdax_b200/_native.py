@@ -13,6 +13,11 @@ import torch
 from qdax_b200 import _lib
 from qdax_b200._lib import CvtIndexDesc, GridDesc, call
 
+import os as _os
+
+DEBUG_SYNC = _os.environ.get("QDX_DEBUG_SYNC", "0") not in ("", "0")     # API boundaries synchronise and check the device error flag
+PEER_TIMEOUT_MS = int(_os.environ.get("QDX_PEER_TIMEOUT_MS", "30000"))    # p2p exchange: how long a rank waits for its peers' keys
+
 TASK_IDS = {None: -1, "none": -1, "arm": 0, "rastrigin": 1, "sphere": 2}
 KEYMODE_KEEP, KEYMODE_UPDATE, KEYMODE_SCAN, KEYMODE_DIST_UPDATE, KEYMODE_EMIT = 0, 1, 2, 3, 4
 
@@ -43,6 +48,26 @@ def key_words(key) -> Tuple[int, int]:
 
 
 # ------------------------------------------------------------------------------------------ workspace
+class _ErrSlots:
+    """Pool of int32 slots in pinned host memory (one cudaHostAlloc per 1024 slots, not one per workspace)."""
+
+    chunks: list = []
+    free: list = []
+
+    @classmethod
+    def take(cls):
+        if not cls.free:
+            t = torch.zeros(1024, dtype=torch.int32).pin_memory()
+            a = t.numpy()
+            cls.chunks.append(t)
+            cls.free.extend((t, a[i:i + 1], t.data_ptr() + 4 * i) for i in range(1024))
+        return cls.free.pop()
+
+    @classmethod
+    def give(cls, slot) -> None:
+        cls.free.append(slot)
+
+
 class Workspace:
     """Per-repertoire device workspace: selection segments, key chain, 64-bit insertion key table."""
 
@@ -57,6 +82,17 @@ class Workspace:
         # fitness array), so a steady-state generation needs no prepare launch.
         self.sel_valid = False
         self.xchg: Optional["PeerExchange"] = None
+        # host mirror of the sticky device error flag: one int32 in pinned host memory that the kernels write when they
+        # raise the flag, polled (never waited for) at the API boundaries -- raise_if_error()
+        self._err_slot = _ErrSlots.take()
+        self._err_np = self._err_slot[1]
+        self._err_np[0] = 0
+        call("qdx_workspace_set_error_mirror", _ptr(self.buf), C.c_void_p(self._err_slot[2]), _stream())
+
+    def __del__(self):
+        slot = getattr(self, "_err_slot", None)
+        if slot is not None:
+            _ErrSlots.give(slot)        # the device buffer dies with this object; stream order keeps late writers off a reused slot
 
     @property
     def ptr(self) -> C.c_void_p:
@@ -83,7 +119,18 @@ class Workspace:
         return np.array(list(ck), dtype=np.uint32), np.array(list(m), dtype=np.float32), int(err.value)
 
     def check(self) -> None:
+        """Blocking: synchronise with the stream and raise if the device error flag is set."""
         _, _, err = self.read()
+        if err != 0:
+            raise _lib.QdxError("device", err)
+
+    def raise_if_error(self) -> None:
+        """Non-blocking: raise if a kernel that has already run reported an error (host mirror).  Called at every API
+        boundary of the repertoire / drivers, so a device-side error surfaces at the latest one call after it happened
+        (immediately in debug mode, QDX_DEBUG_SYNC=1, where the boundaries call check())."""
+        if DEBUG_SYNC:
+            self.check()
+        err = int(self._err_np[0])
         if err != 0:
             raise _lib.QdxError("device", err)
 
@@ -322,11 +369,12 @@ def xchg_push(ws: Workspace, gen_keys) -> None:
 
 def elect_winners(ws: Workspace, rep_g: torch.Tensor, task: str, desc_dim: int, B_dev: int, nranks: int, iso_sigma: float,
                   line_sigma: float, minval, maxval, first_wins: bool, stage_g, stage_f, stage_d, wait_peers: bool = False) -> None:
+    """wait_peers: acquire-spin on the peers' arrival flags for at most PEER_TIMEOUT_MS (then QDX_ERR_PEER_TIMEOUT)."""
     K, D = rep_g.shape
     call("qdx_elect_winners", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim), C.c_int64(B_dev),
          C.c_int32(nranks), _ptr(rep_g), C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None),
          C.c_float(minval or 0.0), C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(bool(first_wins)),
-         _ptr(stage_g), _ptr(stage_f), _ptr(stage_d), C.c_int32(bool(wait_peers)), _stream())
+         _ptr(stage_g), _ptr(stage_f), _ptr(stage_d), C.c_int32(PEER_TIMEOUT_MS if wait_peers else 0), _stream())
 
 
 def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: int, iso_sigma: float, line_sigma: float, minval,
@@ -346,6 +394,63 @@ def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, l
          C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim),
          _grid_ptr(grid), C.c_int32(bool(offer)), C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _ptr(out_g), _ptr(out_f),
          _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _index_ptr(index), _stream())
+
+
+class GenerationStep:
+    """A filled qdx_step_desc + everything it points at (kept alive here): one generation = ONE C-ABI call
+    (qdx_map_elites_step).  Built once per (repertoire buffers, offspring buffers, configuration) and reused while the
+    repertoire is updated in place."""
+
+    def __init__(self, rep_g, rep_f, rep_d, centroids, ws: Workspace, B: int, cfg: dict, grid: Optional[Grid], index: Optional[CvtIndex],
+                 first_wins: bool, buf: dict, rank: int = 0, nranks: int = 1, stage=None):
+        K, D = rep_g.shape
+        Dd = cfg["desc_dim"]
+        d = _lib.StepDesc()
+        self.keep = [rep_g, rep_f, rep_d, centroids, ws, buf, grid, index, stage]
+        d.rep_genotypes, d.rep_fitness, d.rep_desc, d.centroids, d.ws = rep_g.data_ptr(), rep_f.data_ptr(), rep_d.data_ptr(), centroids.data_ptr(), ws.buf.data_ptr()
+        d.K, d.D, d.B, d.desc_dim, d.task = K, D, B, Dd, TASK_IDS[cfg["task"]]
+        d.iso_sigma, d.line_sigma = cfg["iso_sigma"], cfg["line_sigma"]
+        d.has_min, d.minval = int(cfg["minval"] is not None), cfg["minval"] or 0.0
+        d.has_max, d.maxval = int(cfg["maxval"] is not None), cfg["maxval"] or 0.0
+        self.launches = 2
+        if grid is not None:
+            d.grid = C.pointer(grid.desc)
+        elif index is not None:
+            d.cvt = C.pointer(index.desc)
+        else:
+            self.launches += 1
+            if TC_MIN_DIM <= Dd <= TC_MAX_DIM and K >= TC_MIN_CENTROIDS:
+                prep = tc_prep_of(centroids)
+                scratch = torch.empty(B + 64, dtype=torch.int32, device=rep_g.device)
+                self.keep += [prep, scratch]
+                d.tc_prep, d.tc_scratch = prep.data_ptr(), scratch.data_ptr()
+                self.launches += 1
+            if nranks > 1:
+                self.launches += 1                      # qdx_xchg_push
+        d.first_wins, d.qd_offset = int(bool(first_wins)), cfg["qd_offset"]
+        d.off_genotypes, d.off_fitness, d.off_desc, d.off_cells = buf["g"].data_ptr(), buf["f"].data_ptr(), buf["d"].data_ptr(), buf["c"].data_ptr()
+        d.rank, d.nranks, d.exchange, d.peer_timeout_ms = rank, nranks, (1 if nranks > 1 else 0), PEER_TIMEOUT_MS
+        if nranks > 1:
+            sg, sf, sd = stage
+            d.stage_genotypes, d.stage_fitness, d.stage_desc = sg.data_ptr(), sf.data_ptr(), sd.data_ptr()
+            self.launches += 1                          # qdx_elect_winners
+        self.desc = d
+        self.ws = ws
+        self.ref = C.byref(d)
+        self.fn = _lib.lib().qdx_map_elites_step
+
+    def run(self, key_mode: int, key, carry: Optional[np.ndarray], metrics_out: torch.Tensor) -> None:
+        k0, k1 = key_words(key) if key is not None else (0, 0)
+        cio = None
+        if carry is not None:
+            cio = (C.c_uint32 * 2)(int(carry[0]), int(carry[1]))
+        rc = self.fn(self.ref, key_mode, k0, k1, cio, metrics_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.launch_count += self.launches
+        if rc != 0:
+            raise _lib.QdxError("qdx_map_elites_step", rc)
+        if carry is not None:
+            carry[0], carry[1] = cio[0], cio[1]
+        self.ws.sel_valid = True
 
 
 def score(task: str, g: torch.Tensor, desc_dim: int = 2, out_f: Optional[torch.Tensor] = None,

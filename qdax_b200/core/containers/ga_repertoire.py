@@ -29,6 +29,12 @@ class GARepertoire(Repertoire):
             self._ws = _native.Workspace(int(self.fitnesses.shape[0]), self.fitnesses.device)
         return self._ws
 
+    def _raise_if_error(self) -> None:
+        """A device-side error reported by an earlier kernel of this repertoire's workspace (QDX_ERR_*): raised here, at
+        the next API boundary, from the host mirror of the flag -- never blocks (QDX_DEBUG_SYNC=1: synchronises and checks)."""
+        if self._ws is not None:
+            self._ws.raise_if_error()
+
     def _tensor_fields(self):
         return {k: v for k, v in vars(self).items() if isinstance(v, torch.Tensor) and not k.startswith("_")}
 

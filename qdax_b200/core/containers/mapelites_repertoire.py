@@ -168,9 +168,14 @@ class MapElitesRepertoire(GARepertoire):
         current occupant, scatter of genotype / fitness / descriptor / filtered extra scores."""
         if batch_of_extra_scores is None:
             batch_of_extra_scores = {}
+        self._raise_if_error()
         extras = self.filter_extra_scores(batch_of_extra_scores)
         new = self if _donate else self._clone_state()
         rep_g, spec = new._packed_genotypes()
+        if _donate and spec is not None and not tree_util.is_packed_view(new.genotypes, rep_g):
+            # the leaves were not views of one packed buffer (a repertoire built through the constructor / replace()):
+            # pack() copied them, so the rows committed below would land in a temporary -- rebind the leaves to it
+            new.genotypes = tree_util.unpack(rep_g, spec)
         if spec is not None:                      # pytree genotype: one packed row per individual (reference :234-240)
             g2, _ = tree_util.pack(batch_of_genotypes, spec)
             g = g2
@@ -201,6 +206,8 @@ class MapElitesRepertoire(GARepertoire):
             cells_changed = torch.nonzero(added >= 0).reshape(-1)
             src = added[cells_changed].long()
             new.extra_scores = {k: _scatter_rows(new.extra_scores[k], cells_changed, v, src) for k, v in extras.items()}
+        if _native.DEBUG_SYNC:
+            ws.check()
         return new
 
     @classmethod

@@ -42,8 +42,11 @@ class MELSRepertoire(MapElitesRepertoire):
             raise ValueError("MELSRepertoire.add expects fitnesses of shape (batch_size, num_samples)")
         B, S = f_all.shape
         d_all = _native.require_cuda(batch_of_descriptors, "batch_of_descriptors").reshape(B * S, -1)
+        self._raise_if_error()
         new = self if _donate else self._clone_state()
         rep_g, spec = new._packed_genotypes()
+        if _donate and spec is not None and not tree_util.is_packed_view(new.genotypes, rep_g):
+            new.genotypes = tree_util.unpack(rep_g, spec)        # foreign leaves were copied by pack(): rebind to the packed buffer
         if spec is not None:
             g2, _ = tree_util.pack(batch_of_genotypes, spec)
         else:
@@ -71,6 +74,8 @@ class MELSRepertoire(MapElitesRepertoire):
             cells_changed = torch.nonzero(added >= 0).reshape(-1)
             src = added[cells_changed].long()
             new.extra_scores = {k: _scatter_rows(new.extra_scores[k], cells_changed, v, src) for k, v in extras.items()}
+        if _native.DEBUG_SYNC:
+            ws.check()
         return new
 
     @classmethod

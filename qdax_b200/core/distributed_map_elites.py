@@ -104,6 +104,13 @@ class DistributedMAPElites(MAPElites):
                     self._exchange, p2p = "regen", False
             if p2p:
                 self._xchg.attach(ws)
+        ws.raise_if_error()            # sticky device error of an earlier generation (e.g. QDX_ERR_PEER_TIMEOUT): host mirror, never blocks
+        if p2p and self._timeline is None:
+            # the whole generation (generate -> [cells -> publish] -> elect -> commit) behind ONE C-ABI call
+            step = self._generation_step(rep, cfg, ws, rep_f, rank, R, lambda: _stage_views(gb["stage"], D, Dd))
+            _native.ensure_selection(rep_f, ws)
+            step.run(key_mode, key, None, metrics_out)
+            return
         gen_keys = _native.host_generation_keys(key_mode, key)
         self._mark("begin")
         if self._exchange == "regen" and R > 1:
@@ -209,7 +216,19 @@ class DistributedMAPElites(MAPElites):
                 rep, emitter_state, md = self.update(rep, emitter_state, subkey)
                 out.append(torch.stack([md["qd_score"], md["max_fitness"], md["coverage"], md["coverage"] * 0]))
         metrics = torch.stack(out) if out else torch.empty((0, 4))
+        if cfg is not None:
+            self.check_errors(rep)
         return (rep, emitter_state, key), self._metrics_dict(metrics)
+
+    def check_errors(self, repertoire: MapElitesRepertoire) -> None:
+        """Blocking: read this rank's device error flag and all-reduce it, so that a rank-local failure (a peer that did not
+        arrive in time, QDX_ERR_PEER_TIMEOUT; a bad index) raises on EVERY rank together instead of leaving the others to
+        run on with diverged replicas.  Called at the end of every scan; call it after a loop of update()s as well."""
+        _, _, err = repertoire._workspace().read()
+        worst = parallel.all_reduce_min_int(err, repertoire.fitnesses.device, self._group)
+        if worst != 0:
+            from qdax_b200._lib import QdxError
+            raise QdxError("DistributedMAPElites (rank %d reports %d)" % (parallel.world(self._group)[0], err), worst)
 
     def get_distributed_init_fn(self, centroids, devices: Optional[List[Any]] = None) -> Callable:
         """reference :163-179.  One process per GPU: the returned function is called by every rank."""

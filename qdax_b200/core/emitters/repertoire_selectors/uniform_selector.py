@@ -25,6 +25,7 @@ class UniformSelector(Selector):
         if f.dim() == 2 and f.shape[1] != 1:
             raise NotImplementedError("multi-objective fitnesses are outside the MAP-Elites hot path")
         ws = rep._workspace()
+        ws.raise_if_error()
         _native.ensure_selection(f.reshape(-1), ws)
         return _native.select_indices(ws, key, num_samples, f.device)
 

@@ -64,9 +64,22 @@ class MAPElites:
         self._repertoire_init = repertoire_init
         self._buffers: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self._timeline: Optional[list] = None   # bench.py: [(label, cuda event)] recorded around each kernel
+        self._step_cache = None                 # (identity of the buffers, _native.GenerationStep, cfg)
+        self._cfg_cache = None                  # (repertoire object, fused configuration)
 
     # ------------------------------------------------------------------------------------------ fused path
     def _fused_config(self, repertoire) -> Optional[dict]:
+        """Configuration of the fused native path for this repertoire, or None (generic path).  Cached per repertoire OBJECT:
+        repertoires are values (`replace` returns a new object), and an in-place (donated) update keeps every property this
+        decision depends on."""
+        c = self._cfg_cache
+        if c is not None and c[0] is repertoire:
+            return c[1]
+        cfg = self._fused_config_uncached(repertoire)
+        self._cfg_cache = (repertoire, cfg)
+        return cfg
+
+    def _fused_config_uncached(self, repertoire) -> Optional[dict]:
         if self._scoring_function is None or not isinstance(self._emitter, MixingEmitter) or type(repertoire) is not MapElitesRepertoire:
             return None
         iso = self._emitter._fused_isoline()
@@ -106,13 +119,21 @@ class MAPElites:
     def _fused_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out: torch.Tensor,
                           carry: Optional[np.ndarray] = None) -> None:
         """One generation in place on `rep` (launch-only; no host synchronisation).  Steady state = two launches:
-        generate (select + variation + scoring + cell + offer) and commit (whose last CTA also leaves the next
-        generation's parent-selection tables in the workspace); the jax.random.split chain runs on the host."""
+        generate (select + variation + scoring + cell + offer) and commit (whose service CTA also leaves the next
+        generation's parent-selection tables in the workspace); the jax.random.split chain runs on the host.  The whole
+        generation is enqueued by ONE C-ABI call (qdx_map_elites_step); the kernel-by-kernel path below is kept for the
+        instrumented pass of bench.py (a CUDA event after every kernel)."""
+        ws = rep._workspace()
+        ws.raise_if_error()                     # sticky device error of an earlier generation (async mirror, never blocks)
+        rep_f = rep.fitnesses.reshape(-1)
+        if self._timeline is None:
+            step = self._generation_step(rep, cfg, ws, rep_f)
+            _native.ensure_selection(rep_f, ws)
+            step.run(key_mode, key, carry, metrics_out)
+            return
         K, D = rep.genotypes.shape
         B = self._emitter.batch_size
         buf = self._offspring_buffers(B, D, cfg["desc_dim"], rep.genotypes.device)
-        ws = rep._workspace()
-        rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
         first = rep.tie_break == "first"
         gen_keys = _native.host_generation_keys(key_mode, key, carry)
@@ -131,6 +152,23 @@ class MAPElites:
         _native.commit(ws, buf["g"], buf["f"], buf["d"], rep.genotypes, rep_f, rep.descriptors, first_wins=first,
                        qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
         self._mark("commit")
+
+    def _generation_step(self, rep: MapElitesRepertoire, cfg: dict, ws, rep_f, rank: int = 0, nranks: int = 1, stage_fn=None):
+        """The filled qdx_step_desc of this (repertoire buffers, configuration), cached while the repertoire is updated in place."""
+        ident = (rep.genotypes.data_ptr(), rep_f.data_ptr(), rep.descriptors.data_ptr(), rep.centroids.data_ptr(), ws.buf.data_ptr(),
+                 rep.tie_break, rank, nranks, id(cfg))
+        cached = self._step_cache
+        if cached is not None and cached[0] == ident:
+            return cached[1]
+        K, D = rep.genotypes.shape
+        B = self._emitter.batch_size
+        buf = self._offspring_buffers(B, D, cfg["desc_dim"], rep.genotypes.device)
+        grid = rep._grid()
+        index = None if grid is not None else _native.cvt_index_of(rep.centroids)
+        step = _native.GenerationStep(rep.genotypes, rep_f, rep.descriptors, rep.centroids, ws, B, cfg, grid, index,
+                                      rep.tie_break == "first", buf, rank, nranks, stage_fn() if stage_fn is not None else None)
+        self._step_cache = (ident, step, cfg)
+        return step
 
     @staticmethod
     def _metrics_dict(m: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t wait_count(QdxWorkspace* ws, int b, uint32_t
         v = *(volatile unsigned long long*)&ws->occ_pub[b];
         if ((uint32_t)(v >> 32) == seq) return (uint32_t)v;
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; return 0u; }
+        if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); return 0u; }
     }
 }
 
@@ -205,6 +205,12 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
     const int nblk = (int)gridDim.x - 1;                     // streaming CTAs; CTA nblk is the service CTA
     const uint32_t seq = *(volatile uint32_t*)&ws->commit_seq + 1u;     // tag of this launch in occ_pub
     QDX_TRACE_MIN(0);                                         // first CTA starts
+    // Multi-GPU apply after a peer timed out (qdx_elect_kernel raised QDX_ERR_PEER_TIMEOUT and the launch completed before
+    // this one started, so every CTA reads the same value): nothing is applied, no table is cleared, the epoch stays.
+    if (mode == 2 && *(volatile int32_t*)&ws->error == QDX_ERR_PEER_TIMEOUT) {
+        if (p.metrics_out && blockIdx.x == 0 && tid < 4) p.metrics_out[tid] = __int_as_float(0x7fc00000);
+        return;
+    }
 
     if ((int)blockIdx.x == nblk) {
         // ---- service CTA: everything that needs the whole grid's phase-1 results but not the row traffic -- metrics
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                 if (mode == 2) i = c;
                 else {
                     i = (int64_t)qdx_key_index(key, p.first_wins) - (int64_t)p.idx_base;
-                    if (i < 0 || i >= p.B) { if (mode == 0) ws->error = QDX_ERR_BAD_INDEX; i = -1; }
+                    if (i < 0 || i >= p.B) { if (mode == 0) qdx_set_error(ws, QDX_ERR_BAD_INDEX); i = -1; }
                 }
             }
             float fcell = -INFINITY;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                 unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
                     unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
+                    if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
                 }
                 __threadfence();
 #endif
@@ -322,6 +328,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
         }
         __syncthreads();
         QDX_TRACE_MAX(3);                                     // last CTA through the grid barrier
+        const bool aborted = *(volatile int32_t*)&ws->error == QDX_ERR_INTERNAL;    // a grid-barrier wait timed out: stream nothing
 
 #if QDX_COMMIT_EARLY
         // ---- phase 2 without a grid barrier: pairs of list indices from a grid-wide counter (one grab ahead); the warp
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             unsigned nb = 0;
             if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
             nb = __shfl_sync(0xffffffffu, nb, 0);
-            bool done = QDX_COMMIT_EXP == 2;
+            bool done = QDX_COMMIT_EXP == 2 || aborted;
             while (!done) {
                 const unsigned cur = nb;
                 if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                                 if (j >= *(volatile unsigned*)&ws->job_count) break;
                             }
                             unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                            if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_INTERNAL; break; }
+                            if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
                         }
                         if (ent) jobs64[j] = 0ull;                    // re-arm the slot for the next launch
                     }
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
         // (JB entries while plenty remain, 1 at the end), so the warps run out of work within a row or two of each other.
         // The grab for the next batch is issued when a batch starts and consumed after its first row, and that batch's
         // list entries are fetched by the lanes then -- both latencies sit behind row traffic already in flight.
-        const unsigned njobs = QDX_COMMIT_EXP == 2 ? 0u : *(volatile unsigned*)&ws->job_count;
+        const unsigned njobs = (QDX_COMMIT_EXP == 2 || aborted) ? 0u : *(volatile unsigned*)&ws->job_count;
         const uint32_t rowbytes = (uint32_t)p.D * 4u;
         const bool bulk = (p.D & 3) == 0;
         const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
@@ -595,6 +602,9 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
     int rc = device_caps(&caps);
     if (rc) return rc;
     const bool aligned = (((uintptr_t)off_genotypes | (uintptr_t)rep_genotypes) & 15u) == 0;
+#ifdef QDX_COMMIT_FORCE_GENERIC     // sanitizer experiment (tools/sanitize.sh): ordinary loads / stores instead of the bulk-copy ring
+    caps.coop = 0;
+#endif
     if (!caps.coop || caps.ctas_per_sm < 1 || ((D & 3) == 0 && !aligned))
         return qdx_launch_commit_generic(ws, K, D, desc_dim, off_genotypes, off_fitness, off_desc, idx_base, B, first_wins, rep_genotypes,
                                          rep_fitness, rep_desc, qd_offset, metrics_out4, added_cells, mode, (cudaStream_t)stream);

@@ -58,6 +58,9 @@ struct QdxWorkspace {
     unsigned long long xchg_peer[QDX_MAX_PEERS];   // exchange buffer of every rank as mapped into THIS process
     int32_t xchg_rank;
     int32_t xchg_nranks;
+    // host mirror of `error` (pinned host memory, UVA; 0 = none): written by whoever raises the flag, so the host learns of a
+    // device-side error without a blocking read-back and without a copy on the stream (qdx_workspace_set_error_mirror)
+    int32_t* err_host;
     // per-CTA partial metrics of the commit kernel, summed in CTA order by the last CTA (deterministic)
     double part_sum[QDX_MAX_COMMIT_CTAS];
     float part_max[QDX_MAX_COMMIT_CTAS];
@@ -72,6 +75,14 @@ struct QdxWorkspace {
     uint32_t job_count;     // entries of the global list of changed cells (reset by the last CTA)
     uint32_t job_next;      // next batch of the list handed out to a streaming warp (reset by the last CTA)
 };
+
+// Raise the sticky device error flag (first error wins on the host mirror: later ones only overwrite the device copy).
+__device__ __forceinline__ void qdx_set_error(void* ws_raw, int32_t code) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    ws->error = code;
+    int32_t* h = ws->err_host;
+    if (h) { *(volatile int32_t*)h = code; __threadfence_system(); }
+}
 
 __host__ __device__ inline size_t qdx_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline size_t qdx_ws_occ_offset() { return qdx_align_up(sizeof(QdxWorkspace), 256); }

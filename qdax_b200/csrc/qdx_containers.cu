@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) qdx_mels_kernel(const int32_t* __restrict
     out_cells[b] = mode; out_f[b] = f; out_spread[b] = spread;
     const bool in_range = mode >= 0 && mode < K;
     for (int k = 0; k < Dd; ++k) out_desc[b * Dd + k] = in_range ? centroids[(int64_t)mode * Dd + k] : 0.0f;
-    if (!in_range) { ((QdxWorkspace*)ws)->error = QDX_ERR_BAD_CELL; return; }
+    if (!in_range) { qdx_set_error(ws, QDX_ERR_BAD_CELL); return; }
     if (f > rep_f[mode] && spread <= rep_spread[mode])
         atomicMax(qdx_ws_keytab(ws, K) + mode, qdx_pack_key(0.0f, (uint32_t)b, first_wins));
 }

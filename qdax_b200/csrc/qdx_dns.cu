@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(256) qdx_dns_gather_kernel(const float* __rest
     const int64_t i = survivors[row];
     const float* s = i < c.P ? pg + i * D : bg + (i - c.P) * D;
     float* o = out_g + row * D;
-    if ((D & 3) == 0) {
+    // 128-bit copies only for 16-byte aligned rows (D % 4 == 0 and aligned bases: an offset view is not)
+    if ((D & 3) == 0 && ((((uintptr_t)pg) | ((uintptr_t)bg) | ((uintptr_t)out_g)) & 15u) == 0) {
         for (int q = lane; q < (D >> 2); q += 32) reinterpret_cast<float4*>(o)[q] = __ldg(reinterpret_cast<const float4*>(s) + q);
     } else {
         for (int d = lane; d < D; d += 32) o[d] = s[d];

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restri
     }
 
     qdx_cta_occupancy_scan(rep_f, K, ws_raw, s_warp);
-    if (t == 0 && (ws->sel.M <= 0 || ws->sel.nseg <= 0)) ws->error = QDX_ERR_EMPTY_REPERTOIRE;
+    if (t == 0 && (ws->sel.M <= 0 || ws->sel.nseg <= 0)) qdx_set_error(ws, QDX_ERR_EMPTY_REPERTOIRE);
 }
 
 // =====================================================================================================
@@ -213,6 +213,19 @@ QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
 
 constexpr int QDX_GEN_WARPS = 4;
 
+#ifndef QDX_GEN_PLAIN_STORE
+#define QDX_GEN_PLAIN_STORE 0
+#endif
+#ifndef QDX_GEN_TRACE
+#define QDX_GEN_TRACE 0       // timing experiments only: first / last CTA start and end of the generate kernel (tools/time_generate.py)
+#endif
+#if QDX_GEN_TRACE
+__device__ unsigned long long g_gen_trace[4];     // min start, max start, min end, max end (globaltimer ns)
+#define QDX_GEN_STAMP(i, op) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); op(&g_gen_trace[i], t_); } } while (0)
+#else
+#define QDX_GEN_STAMP(i, op)
+#endif
+
 // ARM_CLIP: arm.py:27 clips the genotype to [0,1] before scoring; when the variation already clipped to a range
 // inside [0,1] that clip is the identity and is compiled out (bit-identical result).
 template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI>
@@ -221,7 +234,12 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p);
 // MULTI: the packed row is the concatenation of several pytree leaves, each with its own noise key and counter space.
 template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI = false>
 __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(const QdxGenParams p) {
+    QDX_GEN_STAMP(0, atomicMin); QDX_GEN_STAMP(1, atomicMax);
     qdx_generate_body<TASK, GRID_DD, ARM_CLIP, MULTI>(p);
+#if QDX_GEN_TRACE
+    __syncthreads();
+    QDX_GEN_STAMP(2, atomicMin); QDX_GEN_STAMP(3, atomicMax);
+#endif
     // multi-GPU peer-memory exchange: this CTA's offers (and their pushes into the peers) are done; the last CTA of
     // the grid publishes this rank's generation keys and raises its arrival flag in every peer
     if (GRID_DD != 0 && p.offer && p.keys_by_value) {
@@ -245,7 +263,7 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
     if (GRID_DD > 0) for (int i = threadIdx.x; i < p.grid.total_axes; i += blockDim.x) s_axes[i] = p.grid.axes[i];
     __syncthreads();
     if (nseg <= 0) {           // empty repertoire: p = 0/0 in the reference (uniform_selector.py:45)
-        if (blockIdx.x == 0 && threadIdx.x == 0) ((QdxWorkspace*)p.ws)->error = QDX_ERR_EMPTY_REPERTOIRE;
+        if (blockIdx.x == 0 && threadIdx.x == 0) qdx_set_error(p.ws, QDX_ERR_EMPTY_REPERTOIRE);
         return;
     }
 
@@ -331,9 +349,19 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         }
         // ---- phase 3 (issued early): tile -> global through the bulk-copy engine ------------------------
         // writers make their generic-proxy stores visible to the async proxy, then the warp syncs, then issue
+#if QDX_GEN_PLAIN_STORE      // sanitizer experiment (tools/sanitize.sh): the same rows with ordinary 128-bit stores instead of the bulk-copy engine
+        __syncwarp();
+        if (p.out_g)
+            for (int i = lane; i < total_quads; i += 32) {
+                const int rr = (int)(((uint32_t)i * qmagic) >> 20), dq = i - rr * q;
+                *reinterpret_cast<float4*>(p.out_g + (row0 + rr) * D + d0 + (dq << 2)) = *reinterpret_cast<const float4*>(tile + rr * DS + (dq << 2));
+            }
+        if (false) {
+#else
         if (p.out_g) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
         if (p.out_g) {
+#endif
             if (DS == D) {      // tile is the exact global image of nrows consecutive rows: one bulk copy
                 if (lane == 0) qdx_bulk_store(p.out_g + row0 * D, tile, (uint32_t)(nrows * D * 4));
             } else if (valid) {
@@ -618,7 +646,7 @@ __global__ void __launch_bounds__(256) qdx_offer_kernel(const int32_t* __restric
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= B) return;
     const int32_t c = cells[row];
-    if (c < 0 || c >= K) { ((QdxWorkspace*)ws)->error = QDX_ERR_BAD_CELL; return; }
+    if (c < 0 || c >= K) { qdx_set_error(ws, QDX_ERR_BAD_CELL); return; }
     qdx_offer(ws, K, rep_f, c, fit[row], idx_base + (uint32_t)row, first_wins);
 }
 
@@ -637,8 +665,15 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
     //         cell), keep the key table, no metrics                       (multi-GPU winners-only exchange)
     // mode 2: apply -- off_* are staging rows indexed by CELL; reset keys, metrics
     QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    if (mode == 2 && *(volatile int32_t*)&ws->error == QDX_ERR_PEER_TIMEOUT) {       // see qdx_commit_stream_kernel
+        if (metrics_out && blockIdx.x == 0 && threadIdx.x < 4) metrics_out[threadIdx.x] = __int_as_float(0x7fc00000);
+        return;
+    }
     unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
     const int lane = threadIdx.x & 31;
+    // 128-bit row copies need 16-byte aligned rows: D % 4 == 0 AND 16-byte aligned bases (an offset view of a larger buffer
+    // reaches this fallback precisely because it is not)
+    const bool vec_rows = (D & 3) == 0 && ((((uintptr_t)off_g) | ((uintptr_t)rep_g)) & 15u) == 0;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int added = 0, newly = 0;
@@ -655,11 +690,11 @@ __global__ void __launch_bounds__(256) qdx_commit_kernel(void* ws_raw, int64_t K
         if (win) {
             i = (int64_t)qdx_key_index(key, first_wins) - (int64_t)idx_base;
             if (mode == 2) i = cell;
-            else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) ws->error = QDX_ERR_BAD_INDEX; i = -1; }
+            else if (i < 0 || i >= B) { if (mode == 0 && lane == 0) qdx_set_error(ws, QDX_ERR_BAD_INDEX); i = -1; }
         }
         if (i >= 0) {
             const float* srow = off_g + i * D; float* drow = rep_g + cell * D;
-            if ((D & 3) == 0) {
+            if (vec_rows) {
                 const float4* s4 = reinterpret_cast<const float4*>(srow); float4* d4 = reinterpret_cast<float4*>(drow);
                 const int nq = D >> 2;
                 int q = lane;
@@ -787,13 +822,16 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
 #if QDX_XCHG_TRACE
     const unsigned long long tr_t0 = qdx_now();
 #endif
-    if (wait_peers && threadIdx.x < ws->xchg_nranks) {     // acquire-spin on the LOCAL arrival flags (bounded: 2 s)
+    // A peer that never arrives must not be elected around: on timeout the sticky error is raised (host mirror included)
+    // and qdx_commit(mode 2) of this generation does nothing -- the repertoire, the key tables and the epoch stay as they
+    // are, and the host raises QDX_ERR_PEER_TIMEOUT on its next call instead of letting the replicas diverge silently.
+    if (wait_peers && threadIdx.x < ws->xchg_nranks) {     // acquire-spin on the LOCAL arrival flags (bounded: wait_peers ms)
         const unsigned long long* flag = (const unsigned long long*)ws->xchg_peer[ws->xchg_rank] + threadIdx.x;
         const uint32_t want = *(const uint32_t*)((const char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET) + 1u;
         unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while ((int32_t)((uint32_t)qdx_ld_acquire_sys(flag) - want) < 0) {
             unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 2000000000ull) { ws->error = QDX_ERR_PEER_TIMEOUT; break; }
+            if (t1 - t0 > (unsigned long long)wait_peers * 1000000ull) { qdx_set_error(ws, QDX_ERR_PEER_TIMEOUT); break; }
             __nanosleep(64);
         }
     }
@@ -804,6 +842,7 @@ __global__ void __launch_bounds__(256) qdx_elect_kernel(void* ws_raw, int64_t K,
     const unsigned long long tr_t1 = qdx_now();
 #endif
     if (nseg <= 0) return;
+    if (wait_peers && *(volatile int32_t*)&ws->error == QDX_ERR_PEER_TIMEOUT) return;      // this CTA (or an earlier generation) timed out
     const unsigned long long* keytab = qdx_ws_keytab(ws_raw, K);
     const int32_t* __restrict__ occ = qdx_ws_occ(ws_raw);
     const float total = ws->sel.total;
@@ -927,7 +966,7 @@ __global__ void __launch_bounds__(256) qdx_select_kernel(void* ws_raw, QdxKey ke
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num) return;
     if (nseg <= 0) {                           // empty repertoire (p = 0/0 in the reference): flag it, keep indices in range
-        if (i == 0) ((QdxWorkspace*)ws_raw)->error = QDX_ERR_EMPTY_REPERTOIRE;
+        if (i == 0) qdx_set_error(ws_raw, QDX_ERR_EMPTY_REPERTOIRE);
         out[i] = 0; return;
     }
     const QdxKey sub = qdx_split(key, 1);
@@ -942,7 +981,7 @@ __global__ void __launch_bounds__(256) qdx_gather_rows_kernel(const float* __res
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= B) return;
     const float* s = src + (int64_t)idx[row] * D; float* o = out + row * D;
-    if ((D & 3) == 0) {
+    if ((D & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)out)) & 15u) == 0) {
         for (int q = lane; q < (D >> 2); q += 32) reinterpret_cast<float4*>(o)[q] = __ldg(reinterpret_cast<const float4*>(s) + q);
     } else {
         for (int d = lane; d < D; d += 32) o[d] = s[d];
@@ -1132,6 +1171,15 @@ int qdx_launch_commit_generic(void* ws, int64_t K, int64_t D, int32_t desc_dim, 
     return 0;
 }
 
+#if QDX_GEN_TRACE
+extern "C" int qdx_debug_gen_trace(unsigned long long* out4, int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out4) e = cudaMemcpyFromSymbol(out4, g_gen_trace, sizeof(unsigned long long) * 4);
+    if (e == cudaSuccess && reset) { unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull}; e = cudaMemcpyToSymbol(g_gen_trace, init, sizeof(init)); }
+    return (int)e;
+}
+#endif
+
 #if QDX_XCHG_TRACE
 extern "C" int qdx_debug_xchg_trace(unsigned long long* out8, int reset) {
     cudaError_t e = cudaDeviceSynchronize();
@@ -1174,6 +1222,12 @@ int qdx_workspace_copy_carry_key(void* ws, uint32_t* key2_device, int32_t to_wor
     char* carry = (char*)ws + offsetof(QdxWorkspace, carry);
     return (int)(to_workspace ? cudaMemcpyAsync(carry, key2_device, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, S(stream))
                               : cudaMemcpyAsync(key2_device, carry, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, S(stream)));
+}
+
+int qdx_workspace_set_error_mirror(void* ws, int32_t* host_pinned, void* stream) {
+    if (!ws) return QDX_ERR_ARG;
+    // the 8-byte pointer is staged by the runtime before the call returns (pageable source)
+    return (int)cudaMemcpyAsync((char*)ws + offsetof(QdxWorkspace, err_host), &host_pinned, sizeof(host_pinned), cudaMemcpyHostToDevice, S(stream));
 }
 
 int qdx_workspace_read(void* ws, uint32_t* carry_key2, float* metrics4, int32_t* error, void* stream) {
@@ -1220,6 +1274,7 @@ static int generate_impl(const float* rep_genotypes, const float* rep_fitness, c
     if (task == QDX_TASK_ARM && desc_dim != 2) return QDX_ERR_ARG;
     if (task == QDX_TASK_NONE && (!out_genotypes || offer)) return QDX_ERR_ARG;
     if ((uint64_t)idx_base + (uint64_t)B > 0x7FFFFFFFull) return QDX_ERR_ARG;
+    if ((((uintptr_t)rep_genotypes) | ((uintptr_t)out_genotypes)) & 15u) return QDX_ERR_ARG;   // 128-bit parent loads, bulk-copy stores
     if (B == 0) return 0;
     QdxGenParams p;
     memset(&p, 0, sizeof(p));

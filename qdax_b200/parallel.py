@@ -77,3 +77,13 @@ def all_equal(x: torch.Tensor, group=None) -> bool:
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
     return bool(torch.equal(lo, hi))
+
+
+def all_reduce_min_int(value: int, device, group=None) -> int:
+    """min over ranks of a small host integer (QDX_ERR_* codes are negative: the minimum is the worst error any rank saw)."""
+    _, size = world(group)
+    if size == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())

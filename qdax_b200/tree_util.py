@@ -174,6 +174,12 @@ def pack(tree: Any, spec: TreeSpec = None) -> Tuple[torch.Tensor, TreeSpec]:
     return flat, spec
 
 
+def is_packed_view(tree: Any, flat: torch.Tensor) -> bool:
+    """True when every leaf of `tree` is a view `unpack` handed out of the packed buffer `flat` (so writes into `flat` are
+    writes into the tree)."""
+    return all((t := getattr(l, "_qdx_pack", None)) is not None and t[0] is flat for l in tree_leaves(tree))
+
+
 def leaf_table(spec: TreeSpec, keys: np.ndarray):
     """ctypes qdx_leaf_table for the kernels: offsets + the per-leaf noise keys split(key', n_leaves)."""
     from qdax_b200._lib import LeafTable
