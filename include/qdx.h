@@ -88,14 +88,22 @@ int qdx_select_prepare(const float* rep_fitness, int64_t K, void* ws, int32_t ke
  * gen_keys8: the generation keys {sel1, sel2, line, leaf} derived on the host (qdx_host_generation_keys), or NULL
  * to use the keys qdx_select_prepare left in the workspace.
  * cvt: bucket index over non-grid centroids (qdx_cvt_index below, desc_dim <= 3) or NULL; with it the cell assignment
- * (and the offer) of a CVT tessellation is fused like the grid fast path. */
+ * (and the offer) of a CVT tessellation is fused like the grid fast path.
+ * flags: QDX_GEN_ROWS_FIRED_ONLY -- write only the genotype rows of offspring whose offer fired (the only ones
+ * qdx_commit can elect: an offspring that does not beat its cell's occupant is never inserted), instead of streaming all
+ * B rows to HBM; honoured when the offer is fused and D <= 128, else every row is written.  QDX_GEN_OUT_XCHG -- write the
+ * rows into this rank's offspring block of the peer-memory exchange buffer (current epoch parity) instead of out_genotypes
+ * (ignored), and fitness / descriptors into the block as well as into out_fitness / out_desc: qdx_commit(mode 3) on every
+ * rank reads the winners from the blocks. */
+#define QDX_GEN_ROWS_FIRED_ONLY 1
+#define QDX_GEN_OUT_XCHG 2
 struct qdx_cvt_index;
 int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const float* centroids, void* ws, int64_t K,
                  int64_t D, int64_t B, float iso_sigma, float line_sigma, int32_t has_min, float minval, int32_t has_max,
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
                  int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8,
-                 const struct qdx_cvt_index* cvt, void* stream);
+                 const struct qdx_cvt_index* cvt, int32_t flags, void* stream);
 
 /* ---- stage (b) standalone: arm_scoring_function / rastrigin_scoring_function / sphere_scoring_function */
 int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
@@ -147,7 +155,11 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
  * mode 0: offspring rows indexed by (winner index - idx_base).  Modes 1 / 2 split the commit around an exchange
  * for DistributedMAPElites (distributed_map_elites.py:133-146) when only winners travel: mode 1 copies the
  * winners owned by [idx_base, idx_base + B) into per-cell staging rows (rep_* = staging; keys kept, no metrics);
- * mode 2 applies staging rows indexed by cell (off_* = staging), resets the keys and writes the metrics. */
+ * mode 2 applies staging rows indexed by cell (off_* = staging), resets the keys and writes the metrics.
+ * mode 3 (peer-memory exchange with offspring blocks, see qdx_xchg_* below; off_* ignored): waits for every rank's arrival
+ * flag, then commits each cell's winner from its owner's offspring block.
+ * Rows of at most 1 KB (D <= 256) and mode 3 take a lean kernel (ordinary launch, thread = cell, winners copied by their
+ * warp); longer rows stream through the bulk-copy engine under a cooperative launch. */
 int qdx_offer_cells(const int32_t* cells, const float* fitness, int64_t B, int64_t K, void* ws, const float* rep_fitness,
                     uint32_t idx_base, int32_t first_wins, void* stream);
 int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, const float* off_genotypes, const float* off_fitness,
@@ -181,15 +193,23 @@ int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc
  * exchange table AND -- when they improve the cell's local best -- straight into every peer's table (system-scope
  * atomicMax over NVLink, issued by the offering thread inside qdx_generate / qdx_cells*), the last CTA of a fused
  * qdx_generate (offer != 0, gen_keys8 given) publishes this rank's generation keys and raises its arrival flag in every
- * peer (qdx_xchg_push does the same from a 1-thread kernel after un-fused cells kernels), and
- * qdx_elect_winners(wait_peers = 1) consumes.  nranks <= 16.  All ranks must call the same sequence of generations (the epoch counter lives on the device).
+ * peer (qdx_xchg_push does the same from a 1-thread kernel after un-fused cells kernels).
+ * With B_dev > 0 the buffer also holds two OFFSPRING BLOCKS (genotype rows B_dev x D, fitness, descriptors; selected by
+ * epoch parity like the key tables): qdx_generate(flags & QDX_GEN_OUT_XCHG) leaves the rank's offspring there, and
+ * qdx_commit(mode 3) on every rank waits for all arrival flags (at most timeout_ms, then QDX_ERR_PEER_TIMEOUT and nothing is
+ * applied) and copies each elected winner straight out of its OWNER's block over NVLink (global offspring index =
+ * rank * B_dev + i) -- the all_gather of the reference reduced to the rows that actually change the repertoire, with no
+ * staging and no recomputation; replicas are bit-identical because every rank copies the same bits.
+ * With B_dev = 0 (keys only) the consumer is qdx_elect_winners(wait_peers > 0), which regenerates the winners instead.
+ * nranks <= 16.  All ranks must call the same sequence of generations (the epoch counter lives on the device).
  * qdx_xchg_attach(nranks = 0) detaches. */
-int qdx_xchg_bytes(int64_t K, int64_t* bytes);
-int qdx_xchg_create(int64_t K, void** buf, void* ipc_handle64);
+int qdx_xchg_bytes(int64_t K, int64_t B_dev, int64_t D, int32_t desc_dim, int64_t* bytes);
+int qdx_xchg_create(int64_t K, int64_t B_dev, int64_t D, int32_t desc_dim, void** buf, void* ipc_handle64);
 int qdx_xchg_open(const void* ipc_handle64, void** peer_buf);
 int qdx_xchg_close(void* peer_buf);
 int qdx_xchg_destroy(void* buf);
-int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, void* stream);
+int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, int64_t B_dev, int64_t D, int32_t desc_dim,
+                    int32_t timeout_ms, void* stream);
 int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream);
 
 /* ---- one whole generation per call: the body of MAPElites.update (qdax/core/map_elites.py:148-195) and, with
@@ -198,8 +218,9 @@ int qdx_xchg_push(void* ws, int64_t K, const uint32_t* gen_keys8, void* stream);
  * order and on `stream`: the jax.random.split chain on the host (qdx_host_generation_keys with key_mode / (k0, k1) /
  * carry_io2), qdx_generate (+ the offer when `grid` or `cvt` describes the tessellation), otherwise qdx_cells_tc (tc_prep
  * and tc_scratch given) or qdx_cells with the offer, then qdx_commit -- or, with nranks > 1 (exchange must be
- * QDX_EXCHANGE_P2P, the workspace attached with qdx_xchg_attach): [qdx_xchg_push ->] qdx_elect_winners(wait_peers = 1) ->
- * qdx_commit(mode 2) through the per-cell staging rows.  Rank r's offspring have global indices [r * B, (r + 1) * B).
+ * QDX_EXCHANGE_P2P, the workspace attached with qdx_xchg_attach and offspring blocks of B rows): qdx_generate writes into
+ * this rank's offspring block, [qdx_xchg_push ->] qdx_commit(mode 3) reads the winners from their owners' blocks.
+ * Rank r's offspring have global indices [r * B, (r + 1) * B).
  * The selection tables of the workspace must describe rep_fitness (qdx_select_prepare once, every qdx_commit afterwards).
  * metrics_out4 (device, optional): {qd_score, max_fitness, coverage, offspring inserted}.  Non-blocking. */
 #define QDX_EXCHANGE_NONE 0
@@ -222,8 +243,6 @@ typedef struct qdx_step_desc {
     int32_t first_wins; float qd_offset;
     float* off_genotypes; float* off_fitness; float* off_desc; int32_t* off_cells;   /* offspring buffers (B rows) */
     int32_t rank, nranks, exchange;     /* 0, 1, QDX_EXCHANGE_NONE on one GPU */
-    int32_t peer_timeout_ms;            /* nranks > 1: how long qdx_elect_winners waits for the peers (<= 0: 30 000) */
-    float* stage_genotypes; float* stage_fitness; float* stage_desc;               /* per-cell staging rows (K), nranks > 1 */
 } qdx_step_desc;
 int qdx_map_elites_step(const qdx_step_desc* step, int32_t key_mode, uint32_t k0, uint32_t k1, uint32_t* carry_io2,
                         float* metrics_out4, void* stream);

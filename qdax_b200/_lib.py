@@ -83,8 +83,7 @@ class StepDesc(C.Structure):
         ("tc_prep", _vp), ("tc_scratch", _vp),
         ("first_wins", _i32), ("qd_offset", _f32),
         ("off_genotypes", _vp), ("off_fitness", _vp), ("off_desc", _vp), ("off_cells", _vp),
-        ("rank", _i32), ("nranks", _i32), ("exchange", _i32), ("peer_timeout_ms", _i32),
-        ("stage_genotypes", _vp), ("stage_fitness", _vp), ("stage_desc", _vp),
+        ("rank", _i32), ("nranks", _i32), ("exchange", _i32),
     ]
 
 
@@ -101,15 +100,15 @@ PROTOTYPES = {
     "qdx_select_prepare": [_vp, _i64, _vp, _i32, _u32, _u32, _i32, _vp],
     "qdx_regenerate_winners": [_vp, _i64, _i64, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp],
     "qdx_generate": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _i32,
-                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(CvtIndexDesc), _vp],
+                     C.POINTER(GridDesc), _i32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32), C.POINTER(CvtIndexDesc), _i32, _vp],
     "qdx_elect_winners": [_vp, _i64, _i64, _i32, _i32, _i64, _i32, _vp, _f32, _f32, _i32, _f32, _i32, _f32, _i32, _vp, _vp, _vp,
                           _i32, _vp],
-    "qdx_xchg_bytes": [_i64, C.POINTER(_i64)],
-    "qdx_xchg_create": [_i64, C.POINTER(_vp), _vp],
+    "qdx_xchg_bytes": [_i64, _i64, _i64, _i32, C.POINTER(_i64)],
+    "qdx_xchg_create": [_i64, _i64, _i64, _i32, C.POINTER(_vp), _vp],
     "qdx_xchg_open": [_vp, C.POINTER(_vp)],
     "qdx_xchg_close": [_vp],
     "qdx_xchg_destroy": [_vp],
-    "qdx_xchg_attach": [_vp, _i32, _i32, C.POINTER(_vp), _vp],
+    "qdx_xchg_attach": [_vp, _i32, _i32, C.POINTER(_vp), _i64, _i64, _i32, _i32, _vp],
     "qdx_xchg_push": [_vp, _i64, C.POINTER(_u32), _vp],
     "qdx_map_elites_step": [C.POINTER(StepDesc), _i32, _u32, _u32, C.POINTER(_u32), _vp, _vp],
     "qdx_host_split": [_u32, _u32, _i32, _vp],

@@ -91,7 +91,7 @@ class Workspace:
 
     def __del__(self):
         slot = getattr(self, "_err_slot", None)
-        if slot is not None:
+        if slot is not None and _ErrSlots is not None:      # (None while the interpreter shuts down)
             _ErrSlots.give(slot)        # the device buffer dies with this object; stream order keeps late writers off a reused slot
 
     @property
@@ -307,18 +307,21 @@ class PeerExchange:
     handles around (all_gather_object) and for the set-up barrier.  `attach(ws)` records the mappings in a workspace;
     the generation counter lives in the buffer itself, so workspaces may come and go (cloned repertoires)."""
 
-    def __init__(self, K: int, group=None):
+    def __init__(self, K: int, group=None, B_dev: int = 0, D: int = 0, desc_dim: int = 0):
+        """B_dev > 0: the buffer also holds this rank's two offspring blocks (rows B_dev x D, fitness, descriptors), which
+        the peers read the winners from (qdx_commit mode 3)."""
         import torch.distributed as dist
 
         self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
         self.K = K
+        self.shape = (int(B_dev), int(D), int(desc_dim))
         self.local = C.c_void_p(0)
         self.peers = (C.c_void_p * self.size)()
         self._opened = []
         handle = (C.c_char * 64)()
         err: Optional[Exception] = None
         try:
-            call("qdx_xchg_create", C.c_int64(K), C.byref(self.local), C.cast(handle, C.c_void_p))
+            call("qdx_xchg_create", C.c_int64(K), C.c_int64(B_dev), C.c_int64(D), C.c_int32(desc_dim), C.byref(self.local), C.cast(handle, C.c_void_p))
         except _lib.QdxError as e:
             err = e
         handles = [None] * self.size
@@ -350,7 +353,8 @@ class PeerExchange:
         if ws.xchg is not self:
             if ws.K != self.K:
                 raise ValueError("exchange buffers were created for a different number of cells")
-            call("qdx_xchg_attach", ws.ptr, C.c_int32(self.rank), C.c_int32(self.size), self.peers, _stream())
+            call("qdx_xchg_attach", ws.ptr, C.c_int32(self.rank), C.c_int32(self.size), self.peers, C.c_int64(self.shape[0]),
+                 C.c_int64(self.shape[1]), C.c_int32(self.shape[2]), C.c_int32(PEER_TIMEOUT_MS), _stream())
             ws.xchg = self
 
     def close(self) -> None:
@@ -387,13 +391,16 @@ def regenerate_winners(ws: Workspace, rep_g: torch.Tensor, B_dev: int, nranks: i
 
 def generate(rep_g, rep_f, centroids, ws: Workspace, B: int, iso_sigma: float, line_sigma: float, minval, maxval,
              task: Optional[str], desc_dim: int, grid: Optional[Grid], offer: bool, idx_base: int, first_wins: bool,
-             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None, gen_keys=None, index: Optional[CvtIndex] = None) -> None:
+             out_g, out_f, out_d, out_cells=None, out_p1=None, out_p2=None, gen_keys=None, index: Optional[CvtIndex] = None,
+             fired_rows_only: bool = False, out_xchg: bool = False) -> None:
+    """fired_rows_only / out_xchg: QDX_GEN_ROWS_FIRED_ONLY / QDX_GEN_OUT_XCHG of include/qdx.h."""
     K, D = rep_g.shape
     call("qdx_generate", _ptr(rep_g), _ptr(rep_f), _ptr(centroids), ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int64(B),
          C.c_float(iso_sigma), C.c_float(line_sigma), C.c_int32(minval is not None), C.c_float(minval or 0.0),
          C.c_int32(maxval is not None), C.c_float(maxval or 0.0), C.c_int32(TASK_IDS[task]), C.c_int32(desc_dim),
          _grid_ptr(grid), C.c_int32(bool(offer)), C.c_uint32(idx_base), C.c_int32(bool(first_wins)), _ptr(out_g), _ptr(out_f),
-         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _index_ptr(index), _stream())
+         _ptr(out_d), _ptr(out_cells), _ptr(out_p1), _ptr(out_p2), gen_keys, _index_ptr(index),
+         C.c_int32((1 if fired_rows_only else 0) | (2 if out_xchg else 0)), _stream())
 
 
 class GenerationStep:
@@ -402,11 +409,11 @@ class GenerationStep:
     repertoire is updated in place."""
 
     def __init__(self, rep_g, rep_f, rep_d, centroids, ws: Workspace, B: int, cfg: dict, grid: Optional[Grid], index: Optional[CvtIndex],
-                 first_wins: bool, buf: dict, rank: int = 0, nranks: int = 1, stage=None):
+                 first_wins: bool, buf: dict, rank: int = 0, nranks: int = 1):
         K, D = rep_g.shape
         Dd = cfg["desc_dim"]
         d = _lib.StepDesc()
-        self.keep = [rep_g, rep_f, rep_d, centroids, ws, buf, grid, index, stage]
+        self.keep = [rep_g, rep_f, rep_d, centroids, ws, buf, grid, index]
         d.rep_genotypes, d.rep_fitness, d.rep_desc, d.centroids, d.ws = rep_g.data_ptr(), rep_f.data_ptr(), rep_d.data_ptr(), centroids.data_ptr(), ws.buf.data_ptr()
         d.K, d.D, d.B, d.desc_dim, d.task = K, D, B, Dd, TASK_IDS[cfg["task"]]
         d.iso_sigma, d.line_sigma = cfg["iso_sigma"], cfg["line_sigma"]
@@ -429,11 +436,7 @@ class GenerationStep:
                 self.launches += 1                      # qdx_xchg_push
         d.first_wins, d.qd_offset = int(bool(first_wins)), cfg["qd_offset"]
         d.off_genotypes, d.off_fitness, d.off_desc, d.off_cells = buf["g"].data_ptr(), buf["f"].data_ptr(), buf["d"].data_ptr(), buf["c"].data_ptr()
-        d.rank, d.nranks, d.exchange, d.peer_timeout_ms = rank, nranks, (1 if nranks > 1 else 0), PEER_TIMEOUT_MS
-        if nranks > 1:
-            sg, sf, sd = stage
-            d.stage_genotypes, d.stage_fitness, d.stage_desc = sg.data_ptr(), sf.data_ptr(), sd.data_ptr()
-            self.launches += 1                          # qdx_elect_winners
+        d.rank, d.nranks, d.exchange = rank, nranks, (1 if nranks > 1 else 0)
         self.desc = d
         self.ws = ws
         self.ref = C.byref(d)
@@ -530,7 +533,7 @@ def commit(ws: Workspace, off_g, off_f, off_d, rep_g, rep_f, rep_d, idx_base: in
            mode: int = 0) -> None:
     K, D = rep_g.shape
     call("qdx_commit", ws.ptr, C.c_int64(K), C.c_int64(D), C.c_int32(rep_d.shape[1]), _ptr(off_g), _ptr(off_f), _ptr(off_d),
-         C.c_uint32(idx_base), C.c_int64(off_f.numel()), C.c_int32(bool(first_wins)), _ptr(rep_g), _ptr(rep_f), _ptr(rep_d),
+         C.c_uint32(idx_base), C.c_int64(0 if off_f is None else off_f.numel()), C.c_int32(bool(first_wins)), _ptr(rep_g), _ptr(rep_f), _ptr(rep_d),
          C.c_float(qd_offset), _ptr(metrics_out), _ptr(added_cells), C.c_int32(mode), _stream())
     if mode != 1:
         ws.sel_valid = True     # the last CTA of the commit kernel rescanned rep_f

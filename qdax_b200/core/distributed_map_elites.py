@@ -12,13 +12,15 @@ rank * B_dev + i), same per-rank key chain (`key, subkey = split(key)`; emit(sub
                         rank's generation keys in tail slots; every rank then REGENERATES the winners from (owner's
                         keys, local index) -- the RNG is counter-based and the repertoire replicated -- scores them
                         and commits.  No genotype crosses NVLink.
-  exchange="p2p"        the regen exchange without a collective library, fused into the compute: an offer that improves
-                        its cell's local best is max-merged by the offering thread straight into every peer's key table
-                        (system-scope 64-bit atomicMax over NVLink; buffers mapped with cudaIpc, double-buffered by
-                        generation parity); the last CTA of the generate kernel publishes the rank's generation keys
-                        and raises an arrival flag in every peer; the elect kernel acquire-spins on its local flags,
-                        then regenerates + scores the winners.  generate -> elect -> commit: three launches, no host
-                        involvement, no collective.
+  exchange="p2p"        no collective library, the exchange is fused into the two kernels of a generation: an offer that
+                        improves its cell's local best is max-merged by the offering thread straight into every peer's
+                        key table (system-scope 64-bit atomicMax over NVLink; buffers mapped with cudaIpc,
+                        double-buffered by generation parity) and its genotype row is left in the rank's offspring block
+                        of the same buffer; the last CTA of the generate kernel raises an arrival flag in every peer; the
+                        commit kernel acquire-spins on its local flags, then copies every elected winner straight out
+                        of its OWNER's offspring block (NVLink loads) -- the reference's all_gather reduced to the rows
+                        that change the repertoire.  generate -> commit: two launches (one C-ABI call), no host
+                        involvement, no collective, no recomputation: every rank copies the same bits.
   exchange="winners"    only what can change the repertoire travels: each rank offers its shard into its local
                         64-bit key table, one all-reduce(max) of the K keys elects the global per-cell winners
                         (the global best of a cell is always a local best), winners' rows are merged through a
@@ -68,16 +70,17 @@ class DistributedMAPElites(MAPElites):
                                                    fitnesses=fitnesses, descriptors=descriptors, extra_scores=extra_scores)
         return repertoire, emitter_state, self._metrics_function(repertoire)
 
-    def _gather_buffers(self, R: int, B: int, D: int, Dd: int, K: int, device) -> Dict[str, torch.Tensor]:
-        k = (R, B, D, Dd, K, str(device))
+    def _gather_buffers(self, R: int, B: int, D: int, Dd: int, K: int, device, kind: str) -> Dict[str, torch.Tensor]:
+        """kind "gather": receive buffers of the all-gather exchange; "stage": per-cell staging rows of winners / regen."""
+        k = (kind, R, B, D, Dd, K, str(device))
         if k not in self._dist_buffers:
             f32, i32 = torch.float32, torch.int32
-            self._dist_buffers[k] = {
-                "G": torch.empty((R * B, D), dtype=f32, device=device), "F": torch.empty((R * B,), dtype=f32, device=device),
-                "Dn": torch.empty((R * B, Dd), dtype=f32, device=device), "C": torch.empty((R * B,), dtype=i32, device=device),
-                # staging rows by cell for the winners-only exchange: [genotype | descriptor | fitness] per cell
-                "stage": torch.zeros((K, D + Dd + 1), dtype=f32, device=device),
-            }
+            if kind == "gather":
+                self._dist_buffers[k] = {
+                    "G": torch.empty((R * B, D), dtype=f32, device=device), "F": torch.empty((R * B,), dtype=f32, device=device),
+                    "Dn": torch.empty((R * B, Dd), dtype=f32, device=device), "C": torch.empty((R * B,), dtype=i32, device=device)}
+            else:   # staging rows by cell: [genotype | descriptor | fitness] per cell
+                self._dist_buffers[k] = {"stage": torch.zeros((K, D + Dd + 1), dtype=f32, device=device)}
         return self._dist_buffers[k]
 
     def _fused_distributed_generation(self, rep: MapElitesRepertoire, cfg: dict, key_mode: int, key, metrics_out) -> None:
@@ -87,7 +90,6 @@ class DistributedMAPElites(MAPElites):
         Dd = cfg["desc_dim"]
         dev = rep.genotypes.device
         buf = self._offspring_buffers(B, D, Dd, dev)
-        gb = self._gather_buffers(R, B, D, Dd, K, dev)
         ws = rep._workspace()
         rep_f = rep.fitnesses.reshape(-1)
         grid = rep._grid()
@@ -96,9 +98,11 @@ class DistributedMAPElites(MAPElites):
         p2p = self._exchange == "p2p" and R > 1
         base = rank * B
         if p2p:
-            if self._xchg is None or self._xchg.K != K:
+            if self._xchg is None or self._xchg.K != K or self._xchg.shape != (B, D, Dd):
                 try:
-                    self._xchg = _native.PeerExchange(K, self._group)
+                    if self._xchg is not None:
+                        self._xchg.close()
+                    self._xchg = _native.PeerExchange(K, self._group, B, D, Dd)
                 except _native.PeerExchangeUnavailable as e:     # same decision on every rank: NCCL carries the keys instead
                     self.exchange_fallback = f"p2p unavailable ({e}); using regen"
                     self._exchange, p2p = "regen", False
@@ -107,7 +111,7 @@ class DistributedMAPElites(MAPElites):
         ws.raise_if_error()            # sticky device error of an earlier generation (e.g. QDX_ERR_PEER_TIMEOUT): host mirror, never blocks
         if p2p and self._timeline is None:
             # the whole generation (generate -> [cells -> publish] -> elect -> commit) behind ONE C-ABI call
-            step = self._generation_step(rep, cfg, ws, rep_f, rank, R, lambda: _stage_views(gb["stage"], D, Dd))
+            step = self._generation_step(rep, cfg, ws, rep_f, rank, R)
             _native.ensure_selection(rep_f, ws)
             step.run(key_mode, key, None, metrics_out)
             return
@@ -124,11 +128,12 @@ class DistributedMAPElites(MAPElites):
         fused_cells = grid is not None or index is not None
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], Dd, grid, winners and fused_cells, base, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index)
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index, fired_rows_only=p2p, out_xchg=p2p)
         if not fused_cells:   # cell assignment stays sharded: each rank assigns only its own offspring
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=winners, idx_base=base, first_wins=first, out=buf["c"])
         self._mark("generate")
         if not winners:
+            gb = self._gather_buffers(R, B, D, Dd, K, dev, "gather")
             G = parallel.all_gather_rows(buf["g"], self._group, gb["G"] if R > 1 else None)
             F = parallel.all_gather_rows(buf["f"], self._group, gb["F"] if R > 1 else None)
             Dn = parallel.all_gather_rows(buf["d"], self._group, gb["Dn"] if R > 1 else None)
@@ -144,19 +149,25 @@ class DistributedMAPElites(MAPElites):
                            qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
             self._mark("commit")
             return
-        st = gb["stage"]
+        if p2p:
+            # the offers already pushed their keys into every peer's table (qdx_offer) and the rows of the fired offers sit in
+            # this rank's offspring block; with fused cell assignment the last CTA of the generate kernel also raised the
+            # arrival flags, otherwise a 1-thread kernel does.  The commit waits for every rank's flag and reads each
+            # winner from its owner's block over NVLink.
+            if not fused_cells:
+                _native.xchg_push(ws, gen_keys)
+                self._mark("exchange")
+            _native.commit(ws, None, None, None, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
+                           metrics_out=metrics_out, mode=3)
+            self._mark("commit")
+            return
+        st = self._gather_buffers(R, B, D, Dd, K, dev, "stage")["stage"]
         sg, sd, sf = _stage_views(st, D, Dd)
-        if self._exchange in ("regen", "p2p"):
-            if p2p:
-                # the offers already pushed their records into every peer (qdx_offer); with fused cell assignment the
-                # last CTA of the generate kernel also published keys + arrival flags, otherwise a 1-thread kernel does
-                if not fused_cells:
-                    _native.xchg_push(ws, gen_keys)
-            else:
-                parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
+        if self._exchange == "regen":
+            parallel.all_reduce_max_i64_(ws.keytab(with_key_slots=True), self._group)
             self._mark("exchange_keys")
             _native.elect_winners(ws, rep.genotypes, cfg["task"], Dd, B, R, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
-                                  cfg["maxval"], first, sg, sf, sd, wait_peers=p2p)
+                                  cfg["maxval"], first, sg, sf, sd)
             self._mark("exchange")
             _native.commit(ws, sg, sf, sd, rep.genotypes, rep_f, rep.descriptors, first_wins=first, qd_offset=cfg["qd_offset"],
                            metrics_out=metrics_out, mode=2)

@@ -144,7 +144,7 @@ class MAPElites:
         fused_cells = grid is not None or index is not None
         _native.generate(rep.genotypes, rep_f, rep.centroids, ws, B, cfg["iso_sigma"], cfg["line_sigma"], cfg["minval"],
                          cfg["maxval"], cfg["task"], cfg["desc_dim"], grid, fused_cells, 0, first,
-                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index)
+                         buf["g"], buf["f"], buf["d"], buf["c"], gen_keys=gen_keys, index=index, fired_rows_only=True)
         self._mark("generate")
         if not fused_cells:
             _native.cells(buf["d"], rep.centroids, None, ws, rep_f, buf["f"], offer=True, first_wins=first, out=buf["c"])
@@ -153,7 +153,7 @@ class MAPElites:
                        qd_offset=cfg["qd_offset"], metrics_out=metrics_out)
         self._mark("commit")
 
-    def _generation_step(self, rep: MapElitesRepertoire, cfg: dict, ws, rep_f, rank: int = 0, nranks: int = 1, stage_fn=None):
+    def _generation_step(self, rep: MapElitesRepertoire, cfg: dict, ws, rep_f, rank: int = 0, nranks: int = 1):
         """The filled qdx_step_desc of this (repertoire buffers, configuration), cached while the repertoire is updated in place."""
         ident = (rep.genotypes.data_ptr(), rep_f.data_ptr(), rep.descriptors.data_ptr(), rep.centroids.data_ptr(), ws.buf.data_ptr(),
                  rep.tie_break, rank, nranks, id(cfg))
@@ -166,7 +166,7 @@ class MAPElites:
         grid = rep._grid()
         index = None if grid is not None else _native.cvt_index_of(rep.centroids)
         step = _native.GenerationStep(rep.genotypes, rep_f, rep.descriptors, rep.centroids, ws, B, cfg, grid, index,
-                                      rep.tie_break == "first", buf, rank, nranks, stage_fn() if stage_fn is not None else None)
+                                      rep.tie_break == "first", buf, rank, nranks)
         self._step_cache = (ident, step, cfg)
         return step
 

@@ -51,10 +51,6 @@ constexpr int JB = QDX_COMMIT_JB;      // most list entries (changed cells) per 
 #ifndef QDX_COMMIT_CHUNK
 #define QDX_COMMIT_CHUNK 4096
 #endif
-#ifndef QDX_COMMIT_EARLY
-#define QDX_COMMIT_EARLY 0    // EXPERIMENT, not validated on a GPU yet (round 2): no grid barrier -- list entries are single 64-bit
-#endif                        // words, a warp that grabbed an index waits for that entry only, so CTAs that are done with phase 1
-                              // stream rows while late ones still scan their cells (phase 1 ends between 4 and 7 us after launch)
 #ifndef QDX_COMMIT_EXP
 #define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
 #endif
@@ -286,12 +282,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             unsigned base = 0;
             if (lane == 0 && wb) base = atomicAdd(&ws->job_count, (unsigned)__popc(wb));
             base = __shfl_sync(0xffffffffu, base, 0);
-#if QDX_COMMIT_EARLY
-            if (i >= 0) ((unsigned long long*)job_cell)[base + __popc(wb & ((1u << lane) - 1u))] =
-                            ((unsigned long long)(uint32_t)(c + 1) << 32) | (unsigned long long)(uint32_t)(i + 1);     // 0 = not yet written
-#else
             if (i >= 0) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
-#endif
         }
         // ---- this CTA's partial metrics and occupied count, published BEFORE the grid barrier: the service CTA sums them
         // while the rows stream
@@ -316,102 +307,18 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                 __threadfence();                              // ONE fence: partials + job list before the count and the arrival
                 if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
                 atomicAdd(&ws->cta_arrived, 1u);
-#if !QDX_COMMIT_EARLY
                 unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
                     unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
                 }
                 __threadfence();
-#endif
             }
         }
         __syncthreads();
         QDX_TRACE_MAX(3);                                     // last CTA through the grid barrier
         const bool aborted = *(volatile int32_t*)&ws->error == QDX_ERR_INTERNAL;    // a grid-barrier wait timed out: stream nothing
 
-#if QDX_COMMIT_EARLY
-        // ---- phase 2 without a grid barrier: pairs of list indices from a grid-wide counter (one grab ahead); the warp
-        // waits for each entry to appear, or for "every CTA has arrived and the index is past the end of the list"
-        {
-            unsigned long long* jobs64 = (unsigned long long*)job_cell;
-            const uint32_t rowbytes = (uint32_t)p.D * 4u;
-            const bool bulk = (p.D & 3) == 0;
-            const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
-            unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
-            uint64_t* bars = &s_bar[wid * NST];
-            unsigned long long* sdst = &s_dst[wid * NST];
-            uint32_t* sby = &s_bytes[wid * NST];
-            uint32_t ql = 0, qs = 0;
-            constexpr unsigned JE = 2;
-            unsigned nb = 0;
-            if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
-            nb = __shfl_sync(0xffffffffu, nb, 0);
-            bool done = QDX_COMMIT_EXP == 2 || aborted;
-            while (!done) {
-                const unsigned cur = nb;
-                if (lane == 0) nb = atomicAdd(&ws->job_next, JE);
-                for (unsigned e = 0; e < JE && !done; ++e) {
-                    const unsigned j = cur + e;
-                    unsigned long long ent = 0ull;
-                    if (lane == 0 && j < (unsigned)p.K) {
-                        unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                        for (;;) {
-                            ent = *(volatile unsigned long long*)(jobs64 + j);
-                            if (ent) break;
-                            if (*(volatile unsigned*)&ws->cta_arrived >= (unsigned)nblk) {
-                                __threadfence();
-                                if (j >= *(volatile unsigned*)&ws->job_count) break;
-                            }
-                            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                            if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
-                        }
-                        if (ent) jobs64[j] = 0ull;                    // re-arm the slot for the next launch
-                    }
-                    ent = __shfl_sync(0xffffffffu, ent, 0);
-                    if (!ent) { done = true; break; }
-                    const int32_t cell = (int32_t)(uint32_t)(ent >> 32) - 1, src = (int32_t)(uint32_t)ent - 1;
-                    if (bulk) {
-                        if (lane == 0) {
-                            for (int pc = 0; pc < pieces; ++pc) {
-                                if (ql - qs >= (uint32_t)LEAD) {
-                                    const uint32_t sl = qs % NST;
-                                    mbar_wait(&bars[sl], (qs / NST) & 1u);
-                                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                    if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
-                                    ++qs;
-                                }
-                                const uint32_t sl = ql % NST;
-                                const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
-                                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");
-                                sdst[sl] = (unsigned long long)((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK);
-                                sby[sl] = bytes;
-                                mbar_expect_tx(&bars[sl], bytes);
-                                bulk_g2s(my_stage + sl * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes, &bars[sl]);
-                                ++ql;
-                            }
-                        }
-                        __syncwarp();
-                    } else {
-                        const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
-                        for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
-                    }
-                }
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-            }
-            if (bulk && lane == 0) {
-                while (qs < ql) {
-                    const uint32_t sl = qs % NST;
-                    mbar_wait(&bars[sl], (qs / NST) & 1u);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
-                    ++qs;
-                }
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            }
-            __syncwarp();
-        }
-#else
         // ---- phase 2: the row copies, dealt out in batches of list entries.  SMs differ in their distance to the memory
         // they read and write, so a static deal leaves the slow ones streaming long after the fast ones are done (measured:
         // first CTA done at 36 us, last at 49 us).  Guided self-scheduling instead: warp g of the grid starts on batch g
@@ -496,7 +403,6 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         __syncwarp();
-#endif
         QDX_TRACE_MIN(4); QDX_TRACE_MAX(5);                   // first / last CTA done streaming
         // ---- my slice of the ordered occupied-cell list: offset = sum of the predecessors' counts (all published before
         // the grid barrier, so this is one batched read; doing it before the barrier instead was measured 6-8 us slower --
@@ -550,6 +456,179 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
     }
 }
 
+// =====================================================================================================================
+// Lean commit: the same insertion for the case where there is nothing to stream -- short rows and / or few winners, which
+// is every steady-state generation of the 10^4-cell configurations (~20 winner rows of 400 B: the streaming kernel's
+// cooperative launch, grid barrier, job list and service CTA are ~15 us of fixed latency around 8 KB of traffic).  Ordinary
+// launch, thread = cell (one coalesced pass over keys and fitnesses), the winners of a warp's 32 cells are copied by the
+// whole warp, four rows in flight; per-CTA partial metrics, the last CTA to finish (ticket) reduces them in CTA order and
+// -- only when the set of occupied cells changed -- rebuilds the occupied-cell list and the selection segments.
+//
+// mode 0 / 2 as above.  mode 3 (multi-GPU, peer-memory exchange with offspring blocks): the winner of a cell is read
+// straight out of its OWNER's offspring block (mapped with cudaIpc; NVLink loads), located by its global index
+// rank * B_dev + i; the kernel first acquire-spins on this rank's arrival flags, so the key table is complete and every
+// peer's rows have landed.  Every rank copies the same bits, so the replicas stay identical by construction.
+// =====================================================================================================================
+constexpr int LEAN_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ T* shfl_ptr(T* p, int src) {
+    return (T*)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)p, src);
+}
+
+__global__ void __launch_bounds__(LEAN_THREADS) qdx_commit_lean_kernel(const CommitParams p, int32_t) {
+    QdxWorkspace* ws = (QdxWorkspace*)p.ws;
+    unsigned long long* keytab = qdx_ws_keytab(p.ws, p.K);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int mode = p.mode;
+    __shared__ double s_sum[LEAN_THREADS / 32]; __shared__ float s_max[LEAN_THREADS / 32];
+    __shared__ int s_cnt[LEAN_THREADS / 32], s_nan[LEAN_THREADS / 32], s_add[LEAN_THREADS / 32], s_new[LEAN_THREADS / 32];
+    __shared__ bool s_last;
+    __shared__ int32_t s_scan[33];
+    int parity = 0, R = 1;
+    bool dead = false;                                    // a peer timed out: apply nothing, keep the epoch
+    if (mode == 3) {
+        R = ws->xchg_nranks;
+        parity = qdx_xchg_parity(p.ws);
+        if (tid < R) {                                    // acquire-spin on the LOCAL arrival flags (bounded: wait_ms)
+            const unsigned long long* flag = (const unsigned long long*)ws->xchg_peer[ws->xchg_rank] + tid;
+            const uint32_t want = *(const volatile uint32_t*)((const char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET) + 1u;
+            unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while ((int32_t)((uint32_t)qdx_ld_acquire_sys(flag) - want) < 0) {
+                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > (unsigned long long)(ws->xchg_timeout_ms > 0 ? ws->xchg_timeout_ms : 30000) * 1000000ull) { qdx_set_error(ws, QDX_ERR_PEER_TIMEOUT); break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        dead = *(volatile int32_t*)&ws->error == QDX_ERR_PEER_TIMEOUT;
+    } else if (mode == 2) {
+        dead = *(volatile int32_t*)&ws->error == QDX_ERR_PEER_TIMEOUT;
+    }
+    const bool vec_rows = (p.D & 3) == 0 && (((uintptr_t)p.rep_g) & 15u) == 0 && (mode == 3 || (((uintptr_t)p.off_g) & 15u) == 0);
+    const int nq = p.D >> 2;
+    double sum = 0.0; float mx = -INFINITY; int cnt = 0, nan = 0, added = 0, newly = 0;
+    for (int64_t slab = (int64_t)blockIdx.x * LEAN_THREADS; slab < p.K && !dead; slab += (int64_t)gridDim.x * LEAN_THREADS) {
+        const int64_t c = slab + tid;
+        const bool in = c < p.K;
+        const unsigned long long key = in ? __ldcg(keytab + c) : 0ull;
+        const float cur = in ? __ldcg(p.rep_f + c) : -INFINITY;
+        const float* sg = nullptr; const float* sd = nullptr; const float* sf = nullptr;
+        int64_t i = -1;
+        if (key != 0ull && !qdx_key_is_nan(key)) {           // NaN-poisoned cells accept nobody
+            const int64_t idx = (int64_t)qdx_key_index(key, p.first_wins);
+            if (mode == 2) { i = c; sg = p.off_g; sf = p.off_f; sd = p.off_d; }
+            else if (mode == 3) {
+                const int64_t r = idx / ws->xchg_bdev;
+                if (r < R) { i = idx - r * ws->xchg_bdev; const QdxOffBlock ob = qdx_xchg_block(p.ws, p.K, (int)r, parity); sg = ob.g; sf = ob.f; sd = ob.d; }
+                else qdx_set_error(ws, QDX_ERR_BAD_INDEX);
+            } else {
+                i = idx - (int64_t)p.idx_base; sg = p.off_g; sf = p.off_f; sd = p.off_d;
+                if (i < 0 || i >= p.B) { qdx_set_error(ws, QDX_ERR_BAD_INDEX); i = -1; }
+            }
+        }
+        float fcell = cur;
+        if (i >= 0) {
+            fcell = __ldcg(sf + i);
+            const float* s = sd + i * p.Dd; float* d = p.rep_d + c * p.Dd;
+            for (int d0 = 0; d0 < p.Dd; d0 += 8) {           // all loads of a group ahead of its stores
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (d0 + j < p.Dd) v[j] = __ldcg(s + d0 + j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (d0 + j < p.Dd) d[d0 + j] = v[j];
+            }
+            p.rep_f[c] = fcell;
+            if (p.added_cells) p.added_cells[c] = (int32_t)i;
+            ++added;
+            if (cur == -INFINITY) ++newly;
+        }
+        if (key != 0ull) keytab[c] = 0ull;
+        if (in) {
+            if (fcell != -INFINITY) { sum += (double)fcell; ++cnt; }
+            if (fcell != fcell) nan = 1; else if (fcell > mx) mx = fcell;
+        }
+        // ---- rows of this warp's winners: the whole warp copies them, up to four rows in flight
+        unsigned wb = __ballot_sync(0xffffffffu, i >= 0);
+        const float* my_src = i >= 0 ? sg + i * p.D : nullptr;
+        float* my_dst = i >= 0 ? p.rep_g + c * p.D : nullptr;
+        while (wb) {
+            const float* src[4]; float* dst[4]; int n = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int l = wb ? __ffs(wb) - 1 : 0;
+                src[j] = shfl_ptr(my_src, l); dst[j] = shfl_ptr(my_dst, l);
+                if (wb) { ++n; wb &= wb - 1u; }
+            }
+            if (vec_rows) {
+                for (int q0 = 0; q0 < nq; q0 += 32) {
+                    const int q = q0 + lane;
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < n && q < nq) v[j] = __ldcg(reinterpret_cast<const float4*>(src[j]) + q);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < n && q < nq) reinterpret_cast<float4*>(dst[j])[q] = v[j];
+                }
+            } else {
+                for (int j = 0; j < n; ++j)
+                    for (int d = lane; d < p.D; d += 32) dst[j][d] = __ldcg(src[j] + d);
+            }
+        }
+    }
+    // ---- metrics: per-CTA partials, summed in CTA order by the last CTA to finish (deterministic)
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        added += __shfl_xor_sync(0xffffffffu, added, o); newly += __shfl_xor_sync(0xffffffffu, newly, o);
+    }
+    if (lane == 0) { s_sum[wid] = sum; s_max[wid] = mx; s_cnt[wid] = cnt; s_nan[wid] = nan; s_add[wid] = added; s_new[wid] = newly; }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0, nw = 0;
+        for (int w = 0; w < LEAN_THREADS / 32; ++w) { s += s_sum[w]; m = fmaxf(m, s_max[w]); n += s_cnt[w]; nn |= s_nan[w]; a += s_add[w]; nw += s_new[w]; }
+        ws->part_sum[blockIdx.x] = s; ws->part_max[blockIdx.x] = m; ws->part_cnt[blockIdx.x] = n; ws->part_nan[blockIdx.x] = nn;
+        ws->part_add[blockIdx.x] = a; ws->part_new[blockIdx.x] = nw;
+        __threadfence();
+        s_last = atomicAdd(&ws->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double s = 0.0; float m = -INFINITY; int n = 0, nn = 0, a = 0, nw = 0;
+    for (unsigned b = tid; b < gridDim.x; b += LEAN_THREADS) {
+        s += *(volatile double*)&ws->part_sum[b]; m = fmaxf(m, *(volatile float*)&ws->part_max[b]); n += *(volatile int32_t*)&ws->part_cnt[b];
+        nn |= *(volatile int32_t*)&ws->part_nan[b]; a += *(volatile int32_t*)&ws->part_add[b]; nw += *(volatile int32_t*)&ws->part_new[b];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); n += __shfl_xor_sync(0xffffffffu, n, o);
+        nn |= __shfl_xor_sync(0xffffffffu, nn, o); a += __shfl_xor_sync(0xffffffffu, a, o); nw += __shfl_xor_sync(0xffffffffu, nw, o);
+    }
+    __syncthreads();
+    if (lane == 0) { s_sum[wid] = s; s_max[wid] = m; s_cnt[wid] = n; s_nan[wid] = nn; s_add[wid] = a; s_new[wid] = nw; }
+    __syncthreads();
+    int total_cnt = 0, total_new = 0;
+    for (int w = 0; w < LEAN_THREADS / 32; ++w) { total_cnt += s_cnt[w]; total_new += s_new[w]; }
+    if (tid == 0) {
+        double ts = 0.0; float tm = -INFINITY; int tnn = 0, ta = 0;
+        for (int w = 0; w < LEAN_THREADS / 32; ++w) { ts += s_sum[w]; tm = fmaxf(tm, s_max[w]); tnn |= s_nan[w]; ta += s_add[w]; }
+        float out[4];
+        out[0] = (float)ts + p.qd_offset * (float)total_cnt;            // qd_score   (metrics.py:92-93)
+        out[1] = tnn ? NAN : tm;                                         // max_fitness (:95)
+        out[2] = 100.0f * __fdiv_rn((float)total_cnt, (float)p.K);       // coverage   (:94)
+        out[3] = (float)ta;                                              // offspring inserted by this call
+        if (dead) for (int j = 0; j < 4; ++j) out[j] = __int_as_float(0x7fc00000);
+        for (int j = 0; j < 4; ++j) { ws->metrics[j] = out[j]; if (p.metrics_out) p.metrics_out[j] = out[j]; }
+        ws->ticket = 0u;
+        if (!dead && (mode == 2 || mode == 3) && ws->xchg_nranks > 0) {  // peer-memory exchange: next generation, other tables / blocks
+            uint32_t* ep = (uint32_t*)((char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET);
+            *ep = *ep + 1u;
+        }
+    }
+    // the repertoire is final: leave the NEXT generation's parent selection ready.  The occupied-cell list only changes when a
+    // cell turned from empty to occupied, or when the workspace has not seen this repertoire yet (M mismatch)
+    if (!dead && (total_new != 0 || total_cnt != ws->sel.M || ws->sel.nseg <= 0)) qdx_cta_occupancy_scan(p.rep_f, p.K, p.ws, s_scan);
+}
+
 struct DeviceCaps { int sms; int ctas_per_sm; int coop; };
 
 int device_caps(DeviceCaps* out) {
@@ -596,8 +675,20 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
                           const float* off_desc, uint32_t idx_base, int64_t B, int32_t first_wins, float* rep_genotypes,
                           float* rep_fitness, float* rep_desc, float qd_offset, float* metrics_out4, int32_t* added_cells,
                           int32_t mode, void* stream) {
-    if (!ws || !off_genotypes || !off_fitness || !off_desc || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
-    if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 2) return QDX_ERR_ARG;
+    if (!ws || !rep_genotypes || !rep_fitness || !rep_desc) return QDX_ERR_ARG;
+    if (mode != 3 && (!off_genotypes || !off_fitness || !off_desc)) return QDX_ERR_ARG;      // mode 3 reads the peers' offspring blocks
+    if (K <= 0 || D <= 0 || desc_dim < 1 || B < 0 || mode < 0 || mode > 3) return QDX_ERR_ARG;
+    CommitParams p;
+    p.ws = ws; p.K = K; p.D = (int32_t)D; p.Dd = desc_dim; p.off_g = off_genotypes; p.off_f = off_fitness; p.off_d = off_desc;
+    p.idx_base = idx_base; p.B = B; p.first_wins = first_wins; p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.rep_d = rep_desc;
+    p.qd_offset = qd_offset; p.metrics_out = metrics_out4; p.added_cells = added_cells; p.mode = mode;
+    // short rows (<= 1 KB) or peer sources: nothing to stream, the lean kernel (ordinary launch, thread = cell) is all latency saved
+    if (mode == 3 || (mode != 1 && D <= 256)) {
+        int64_t ctas = (K + LEAN_THREADS - 1) / LEAN_THREADS;
+        if (ctas > QDX_MAX_COMMIT_CTAS) ctas = QDX_MAX_COMMIT_CTAS;
+        qdx_commit_lean_kernel<<<(unsigned)ctas, LEAN_THREADS, 0, (cudaStream_t)stream>>>(p, 0);
+        return (int)cudaGetLastError();
+    }
     DeviceCaps caps;
     int rc = device_caps(&caps);
     if (rc) return rc;
@@ -613,16 +704,7 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
     if (nblk > cap) nblk = cap;
     if (nblk > QDX_MAX_COMMIT_CTAS - 1) nblk = QDX_MAX_COMMIT_CTAS - 1;
     if (nblk < 1) nblk = 1;
-    CommitParams p;
-    p.ws = ws; p.K = K; p.D = (int32_t)D; p.Dd = desc_dim; p.off_g = off_genotypes; p.off_f = off_fitness; p.off_d = off_desc;
-    p.idx_base = idx_base; p.B = B; p.first_wins = first_wins; p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.rep_d = rep_desc;
-    p.qd_offset = qd_offset; p.metrics_out = metrics_out4; p.added_cells = added_cells; p.mode = mode;
     void* args[] = {(void*)&p};
-#if defined(QDX_COMMIT_NOCOOP)      // timing experiment only: co-residency is NOT guaranteed by an ordinary launch
-    qdx_commit_stream_kernel<<<dim3((unsigned)(nblk + 1)), dim3(CW * 32), (size_t)CW * NST * CHUNK, (cudaStream_t)stream>>>(p);
-    (void)args;
-    return (int)cudaGetLastError();
-#endif
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)qdx_commit_stream_kernel, dim3((unsigned)(nblk + 1)), dim3(CW * 32), args,
                                                 (size_t)CW * NST * CHUNK, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : (int)e;

@@ -58,6 +58,13 @@ struct QdxWorkspace {
     unsigned long long xchg_peer[QDX_MAX_PEERS];   // exchange buffer of every rank as mapped into THIS process
     int32_t xchg_rank;
     int32_t xchg_nranks;
+    // offspring blocks of the exchange buffers (0 = none: the regen exchange): every rank keeps the rows of its fired offers
+    // where its peers can read them, so the replicated insertion copies a winner straight from its owner over NVLink
+    int64_t xchg_bdev;      // offspring per rank and generation
+    int32_t xchg_D;
+    int32_t xchg_Dd;
+    int32_t xchg_timeout_ms;   // how long a consumer waits for its peers' arrival flags before it raises QDX_ERR_PEER_TIMEOUT
+    int32_t pad1;
     // host mirror of `error` (pinned host memory, UVA; 0 = none): written by whoever raises the flag, so the host learns of a
     // device-side error without a blocking read-back and without a copy on the stream (qdx_workspace_set_error_mirror)
     int32_t* err_host;
@@ -104,12 +111,40 @@ __host__ __device__ inline int32_t* qdx_ws_occ(void* ws) { return (int32_t*)((ch
 //                        the workspace so that it survives when a cloned repertoire brings a fresh workspace)
 //   then 2 key tables    (K keys + 8 * QDX_MAX_RANKS generation-key slots) x uint64, selected by epoch parity so a
 //                        fast rank may push generation e+1 while this rank still consumes generation e
+#define QDX_XCHG_EPOCH_OFFSET 512
 __host__ __device__ inline size_t qdx_xchg_tab_entries(int64_t K) { return (size_t)K + 8 * QDX_MAX_RANKS; }
 __host__ __device__ inline size_t qdx_xchg_tab_offset(int64_t K, int parity) {
     return 1024 + (size_t)parity * qdx_align_up(qdx_xchg_tab_entries(K) * sizeof(unsigned long long), 256);
 }
-__host__ __device__ inline size_t qdx_xchg_total_bytes(int64_t K) { return qdx_xchg_tab_offset(K, 2); }
-#define QDX_XCHG_EPOCH_OFFSET 512
+// ... followed (B_dev > 0) by 2 offspring blocks, again selected by epoch parity: genotype rows (B_dev x D), fitness (B_dev),
+// descriptors (B_dev x Dd) of this rank's offspring.  A rank starts generation e + 2 only after every rank has raised its
+// flag of generation e + 1, i.e. after every rank has finished applying generation e -- so two blocks suffice.
+__host__ __device__ inline size_t qdx_xchg_block_g_bytes(int64_t B_dev, int64_t D) { return qdx_align_up((size_t)B_dev * (size_t)D * 4, 256); }
+__host__ __device__ inline size_t qdx_xchg_block_f_bytes(int64_t B_dev) { return qdx_align_up((size_t)B_dev * 4, 256); }
+__host__ __device__ inline size_t qdx_xchg_block_bytes(int64_t B_dev, int64_t D, int64_t Dd) {
+    return qdx_xchg_block_g_bytes(B_dev, D) + qdx_xchg_block_f_bytes(B_dev) + qdx_align_up((size_t)B_dev * (size_t)Dd * 4, 256);
+}
+__host__ __device__ inline size_t qdx_xchg_block_offset(int64_t K, int parity, int64_t B_dev, int64_t D, int64_t Dd) {
+    return qdx_xchg_tab_offset(K, 2) + (size_t)parity * qdx_xchg_block_bytes(B_dev, D, Dd);
+}
+__host__ __device__ inline size_t qdx_xchg_total_bytes(int64_t K, int64_t B_dev = 0, int64_t D = 0, int64_t Dd = 0) {
+    return B_dev > 0 ? qdx_xchg_block_offset(K, 2, B_dev, D, Dd) : qdx_xchg_tab_offset(K, 2);
+}
+// offspring block of rank `r` for the current generation, as mapped into THIS process
+struct QdxOffBlock { float* g; float* f; float* d; };
+__device__ __forceinline__ QdxOffBlock qdx_xchg_block(const void* ws_raw, int64_t K, int r, int parity) {
+    const struct QdxWorkspace* ws = (const struct QdxWorkspace*)ws_raw;
+    char* b = (char*)ws->xchg_peer[r] + qdx_xchg_block_offset(K, parity, ws->xchg_bdev, ws->xchg_D, ws->xchg_Dd);
+    QdxOffBlock o;
+    o.g = (float*)b;
+    o.f = (float*)(b + qdx_xchg_block_g_bytes(ws->xchg_bdev, ws->xchg_D));
+    o.d = (float*)(b + qdx_xchg_block_g_bytes(ws->xchg_bdev, ws->xchg_D) + qdx_xchg_block_f_bytes(ws->xchg_bdev));
+    return o;
+}
+__device__ __forceinline__ int qdx_xchg_parity(const void* ws_raw) {
+    const struct QdxWorkspace* ws = (const struct QdxWorkspace*)ws_raw;
+    return (int)(*(const volatile uint32_t*)((const char*)ws->xchg_peer[ws->xchg_rank] + QDX_XCHG_EPOCH_OFFSET) & 1u);
+}
 // The insertion key table of the current generation: inside the workspace on one GPU, inside the exchange buffer
 // (parity of the epoch) when the peer-memory exchange is attached.
 __device__ __forceinline__ unsigned long long* qdx_ws_keytab(void* ws_raw, int64_t K) {
@@ -154,9 +189,11 @@ QDX_DEV uint32_t qdx_key_index(unsigned long long key, int first_wins) {
 // record, so every table ends up holding the global maximum.  (~ln(offers per cell) records per cell at cold start,
 // about one per changed cell in steady state.)  The fence makes the remote atomics visible before this thread's warp
 // reports done (qdx_xchg_warp_done).
-QDX_DEV void qdx_offer(void* ws_raw, int64_t K, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
+// Returns true when the offer was made (the offspring may be elected: its row must exist for the commit).
+QDX_DEV bool qdx_offer(void* ws_raw, int64_t K, const float* rep_f, int32_t c, float f, uint32_t idx, int first_wins) {
     const float cur = __ldg(rep_f + c);
-    if ((f != f) || f > cur) {
+    const bool fire = (f != f) || f > cur;
+    if (fire) {
         const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
         const unsigned long long key = qdx_pack_key(f, idx, first_wins);
         const int R = ws->xchg_nranks;
@@ -173,7 +210,77 @@ QDX_DEV void qdx_offer(void* ws_raw, int64_t K, const float* rep_f, int32_t c, f
             atomicMax((unsigned long long*)((char*)ws_raw + qdx_ws_keytab_offset(K)) + c, key);
         }
     }
+    return fire;
 }
+
+// Occupancy scan by ONE CTA (any multiple of 32 threads, <= 1024): ordered list of occupied cells -> occ[], M, and the
+// selection segments (rebuilt only when M changed).  Warp w owns the contiguous cell range [w*chunk, (w+1)*chunk);
+// 32 cells per step, ballot + popc, every load coalesced and independent of the previous step.  Used by the
+// prepare kernel and by the last CTA of the commit kernel (which leaves the NEXT generation's selection ready, so a
+// steady-state generation needs no prepare launch).  s_warp: >= 33 int32 of shared memory.
+static __device__ __noinline__ void qdx_cta_occupancy_scan(const float* rep_f, int64_t K, void* ws_raw, int32_t* s_warp) {
+    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
+    int32_t* occ = qdx_ws_occ(ws_raw);
+    constexpr int BAL = 2048;                       // ballot words kept in shared memory: K <= 65536 needs no second read
+    __shared__ uint32_t s_bal[BAL];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+    const int64_t chunk = ((K + nw - 1) / nw + 31) / 32 * 32;
+    const int64_t lo = (int64_t)w * chunk, hi = lo + chunk < K ? lo + chunk : K;
+    const bool keep = (K + 31) / 32 <= BAL;
+    // every step's load is independent of the previous step's ballot: 16 loads in flight per lane (the fitness array is
+    // L2-resident, so the scan is latency- not bandwidth-bound)
+    constexpr int U = 16;
+    int32_t cnt = 0;
+    for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned b = __ballot_sync(0xffffffffu, v[u] != -INFINITY);
+            cnt += __popc(b);
+            if (keep && lane == 0 && c0 + 32 * u < hi) s_bal[(c0 >> 5) + u] = b;
+        }
+    }
+    __syncthreads();                       // s_warp may still be in use by the caller
+    if (lane == 0) s_warp[w] = cnt;
+    __syncthreads();
+    if (w == 0) {
+        int32_t v = lane < nw ? s_warp[lane] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        __syncwarp();
+        s_warp[lane] = x - v;
+        if (lane == 31) s_warp[32] = x;
+    }
+    __syncthreads();
+    int32_t pos = s_warp[w];
+    if (keep) {
+        for (int64_t c0 = lo; c0 < hi; c0 += 32) {
+            const unsigned b = s_bal[c0 >> 5];
+            if ((b >> lane) & 1u) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + lane);
+            pos += __popc(b);
+        }
+    } else {
+        for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool o = v[u] != -INFINITY;
+                const unsigned b = __ballot_sync(0xffffffffu, o);
+                if (o) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + 32 * u + lane);
+                pos += __popc(b);
+            }
+        }
+    }
+    if (t == 0) {
+        const int32_t M = s_warp[32];
+        if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
+    }
+}
+
 
 #ifndef QDX_XCHG_TRACE
 #define QDX_XCHG_TRACE 0      // timing experiments only: where a multi-GPU generation's tail goes (qdx_debug_xchg_trace)

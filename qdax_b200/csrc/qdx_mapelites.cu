@@ -36,74 +36,6 @@ __device__ void qdx_derive_gen_keys(QdxKey emit, QdxGenKeys* out) {
     out->leaf = qdx_split(qdx_split(kv, 0), 0);                                          // :220 (one leaf)
 }
 
-// Occupancy scan by ONE CTA (any multiple of 32 threads, <= 1024): ordered list of occupied cells -> occ[], M, and the
-// selection segments (rebuilt only when M changed).  Warp w owns the contiguous cell range [w*chunk, (w+1)*chunk);
-// 32 cells per step, ballot + popc, every load coalesced and independent of the previous step.  Used by the
-// prepare kernel and by the last CTA of the commit kernel (which leaves the NEXT generation's selection ready, so a
-// steady-state generation needs no prepare launch).  s_warp: >= 33 int32 of shared memory.
-__device__ void qdx_cta_occupancy_scan(const float* rep_f, int64_t K, void* ws_raw, int32_t* s_warp) {
-    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
-    int32_t* occ = qdx_ws_occ(ws_raw);
-    constexpr int BAL = 2048;                       // ballot words kept in shared memory: K <= 65536 needs no second read
-    __shared__ uint32_t s_bal[BAL];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
-    const int64_t chunk = ((K + nw - 1) / nw + 31) / 32 * 32;
-    const int64_t lo = (int64_t)w * chunk, hi = lo + chunk < K ? lo + chunk : K;
-    const bool keep = (K + 31) / 32 <= BAL;
-    // every step's load is independent of the previous step's ballot: 16 loads in flight per lane (the fitness array is
-    // L2-resident, so the scan is latency- not bandwidth-bound)
-    constexpr int U = 16;
-    int32_t cnt = 0;
-    for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned b = __ballot_sync(0xffffffffu, v[u] != -INFINITY);
-            cnt += __popc(b);
-            if (keep && lane == 0 && c0 + 32 * u < hi) s_bal[(c0 >> 5) + u] = b;
-        }
-    }
-    __syncthreads();                       // s_warp may still be in use by the caller
-    if (lane == 0) s_warp[w] = cnt;
-    __syncthreads();
-    if (w == 0) {
-        int32_t v = lane < nw ? s_warp[lane] : 0, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        __syncwarp();
-        s_warp[lane] = x - v;
-        if (lane == 31) s_warp[32] = x;
-    }
-    __syncthreads();
-    int32_t pos = s_warp[w];
-    if (keep) {
-        for (int64_t c0 = lo; c0 < hi; c0 += 32) {
-            const unsigned b = s_bal[c0 >> 5];
-            if ((b >> lane) & 1u) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + lane);
-            pos += __popc(b);
-        }
-    } else {
-        for (int64_t c0 = lo; c0 < hi; c0 += 32 * U) {
-            float v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { const int64_t c = c0 + 32 * u + lane; v[u] = c < hi ? __ldcg(rep_f + c) : -INFINITY; }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool o = v[u] != -INFINITY;
-                const unsigned b = __ballot_sync(0xffffffffu, o);
-                if (o) occ[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(c0 + 32 * u + lane);
-                pos += __popc(b);
-            }
-        }
-    }
-    if (t == 0) {
-        const int32_t M = s_warp[32];
-        if (M != ws->sel.M || ws->sel.nseg <= 0) qdx_build_sel(M, &ws->sel);
-    }
-}
-
 // key_mode: 0 keep keys; 1 `key` = key of MAPElites.update; 2 scan step on ws->carry; 3 `key` = key of
 // DistributedMAPElites.update; 4 `key` = emit key.
 __global__ void __launch_bounds__(1024) qdx_prepare_kernel(const float* __restrict__ rep_f, int64_t K, void* ws_raw,
@@ -202,6 +134,8 @@ struct QdxGenParams {
     QdxGrid grid;
     int32_t offer; uint32_t idx_base; int32_t first_wins;
     int32_t keys_by_value; QdxGenKeys keys;          // generation keys derived on the host (qdx_host_generation_keys)
+    int32_t store_mode;                               // 0: every offspring row (bulk copy of the tile); 1: only the rows whose offer fired
+    int32_t out_xchg;                                 // 1: out_g / out_f / out_d = this rank's offspring block of the exchange buffer (epoch parity)
     QdxCvtIndex cvt;                                  // bucket index over non-grid centroids (GRID_DD < 0)
     QdxLeafTab leaves;                                // pytree genotypes (MULTI instantiation only)
 };
@@ -209,6 +143,14 @@ struct QdxGenParams {
 QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                  :: "l"(gptr), "r"((uint32_t)__cvta_generic_to_shared(sptr)), "r"(bytes) : "memory");
+}
+
+// One offspring row, shared memory -> global, by the lane that owns it (store_mode 1: only the rare rows whose offer
+// fired are kept -- in steady state ~0.1 % of them -- instead of streaming the whole 400 B x B offspring buffer to HBM every
+// generation); `sys`: the row will be read by peer GPUs, fence at system scope.
+QDX_DEV void qdx_store_row(float* __restrict__ dst, const float* src_smem, int n, int sys) {
+    for (int d = 0; d < n; d += 4) *reinterpret_cast<float4*>(dst + d) = *reinterpret_cast<const float4*>(src_smem + d);
+    if (sys) __threadfence_system();
 }
 
 constexpr int QDX_GEN_WARPS = 4;
@@ -268,17 +210,28 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
     }
 
     float* tile = s_tiles + (size_t)warp * 32 * DS;
-    const int64_t row0 = ((int64_t)blockIdx.x * QDX_GEN_WARPS + warp) * 32;
-    if (row0 >= p.B) return;
-    const int64_t row = row0 + lane;
-    const bool valid = row < p.B;
-    const int nrows = (p.B - row0) < 32 ? (int)(p.B - row0) : 32;
+    // Persistent grid (at most one resident wave of CTAs): warp w of the grid owns the contiguous rows
+    // [B w / W, B (w + 1) / W) and walks them in tiles of up to 32 rows, so every warp of every SM has work until the very
+    // end of the kernel whatever B is (a grid of ceil(B / 128) CTAs left the SMs 27 % idle during the second "wave" of the
+    // 131 072-row shards of an 8-GPU run), and the per-CTA prologue above is paid once.
+    const int64_t n_warps = (int64_t)gridDim.x * QDX_GEN_WARPS, w_id = (int64_t)blockIdx.x * QDX_GEN_WARPS + warp;
+    const int64_t r_lo = p.B * w_id / n_warps, r_hi = p.B * (w_id + 1) / n_warps;
     const QdxGenKeys keys = p.keys_by_value ? p.keys : ws->keys;
     const int32_t* __restrict__ occ = qdx_ws_occ(p.ws);
     const float total = ws->sel.total;
+    float* out_g = p.out_g; float* const out_f = p.out_f; float* const out_d = p.out_d;
+    float* xf = nullptr; float* xd = nullptr;
+    if (p.out_xchg) {        // multi-GPU: the rows go where the peers can read them (this rank's block of the current epoch parity),
+        const QdxOffBlock ob = qdx_xchg_block(p.ws, p.K, ws->xchg_rank, qdx_xchg_parity(p.ws));      // fitness / descriptors to both places
+        out_g = ob.g; xf = ob.f; xd = ob.d;
+    }
+    for (int64_t row0 = r_lo; row0 < r_hi; row0 += 32) {
+    const int64_t row = row0 + lane;
+    const int nrows = (r_hi - row0) < 32 ? (int)(r_hi - row0) : 32;
+    const bool valid = lane < nrows;
 
     // ---- phase 0: parents + line noise, lane = row --------------------------------------------------
-    // (rows past the end of the batch compute harmless values and never store)
+    // (lanes past the end of the tile compute harmless values and never store)
     int32_t p1, p2; float line;
     {
         float u1 = qdx_unit_float(qdx_bits32(keys.sel1, (uint64_t)row));
@@ -351,21 +304,22 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         // writers make their generic-proxy stores visible to the async proxy, then the warp syncs, then issue
 #if QDX_GEN_PLAIN_STORE      // sanitizer experiment (tools/sanitize.sh): the same rows with ordinary 128-bit stores instead of the bulk-copy engine
         __syncwarp();
-        if (p.out_g)
+        if (out_g && p.store_mode == 0)
             for (int i = lane; i < total_quads; i += 32) {
                 const int rr = (int)(((uint32_t)i * qmagic) >> 20), dq = i - rr * q;
-                *reinterpret_cast<float4*>(p.out_g + (row0 + rr) * D + d0 + (dq << 2)) = *reinterpret_cast<const float4*>(tile + rr * DS + (dq << 2));
+                *reinterpret_cast<float4*>(out_g + (row0 + rr) * D + d0 + (dq << 2)) = *reinterpret_cast<const float4*>(tile + rr * DS + (dq << 2));
             }
         if (false) {
 #else
-        if (p.out_g) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        const bool bulk_rows = out_g && p.store_mode == 0;
+        if (bulk_rows) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (p.out_g) {
+        if (bulk_rows) {
 #endif
             if (DS == D) {      // tile is the exact global image of nrows consecutive rows: one bulk copy
-                if (lane == 0) qdx_bulk_store(p.out_g + row0 * D, tile, (uint32_t)(nrows * D * 4));
+                if (lane == 0) qdx_bulk_store(out_g + row0 * D, tile, (uint32_t)(nrows * D * 4));
             } else if (valid) {
-                qdx_bulk_store(p.out_g + row * D + d0, tile + lane * DS, (uint32_t)(dc * 4));
+                qdx_bulk_store(out_g + row * D + d0, tile + lane * DS, (uint32_t)(dc * 4));
             }
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
@@ -407,14 +361,16 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
                 const float fit = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
                 const float dx = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
                 const float dy = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
-                p.out_f[row] = fit;
-                reinterpret_cast<float2*>(p.out_d)[row] = make_float2(dx, dy);
+                out_f[row] = fit;
+                reinterpret_cast<float2*>(out_d)[row] = make_float2(dx, dy);
+                if (xf) { xf[row] = fit; reinterpret_cast<float2*>(xd)[row] = make_float2(dx, dy); }
                 if (GRID_DD != 0) {
                     float xd[QDX_MAX_GRID_DIM] = {dx, dy, 0.0f, 0.0f};
                     const int32_t cell = GRID_DD > 0 ? qdx_grid_cell<(GRID_DD > 0 ? GRID_DD : 1)>(xd, p.grid, s_axes, p.centroids, p.K)
                                                      : qdx_index_cell<(GRID_DD < 0 ? -GRID_DD : 1)>(xd, p.cvt);
                     if (p.out_cell) p.out_cell[row] = cell;
-                    if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                    if (p.offer && qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins) && p.store_mode == 1)
+                        qdx_store_row(out_g + row * D, xr, dc, p.out_xchg);
                 }
             } else {
                 for (int d = 0; d < dc; d += 4) {
@@ -435,28 +391,38 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
                     for (int j = 0; j < 4; ++j) acc0 = acc0 + term[j];
                 }
                 if (ch == 0) {
-                    for (int j = 0; j < p.desc_dim; ++j) p.out_d[row * p.desc_dim + j] = xr[j];   // desc = first genes
+                    for (int j = 0; j < p.desc_dim; ++j) out_d[row * p.desc_dim + j] = xr[j];   // desc = first genes
+                    if (xd) for (int j = 0; j < p.desc_dim; ++j) xd[row * p.desc_dim + j] = xr[j];
                 }
                 if (ch == nchunks - 1) {
                     float f = acc0;
                     if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
                     const float fit = -f;
-                    p.out_f[row] = fit;
+                    out_f[row] = fit;
+                    if (xf) xf[row] = fit;
                     if (GRID_DD != 0) {
                         float xd[QDX_MAX_GRID_DIM];
 #pragma unroll
-                        for (int j = 0; j < (GRID_DD > 0 ? GRID_DD : -GRID_DD); ++j) xd[j] = p.out_d[row * p.desc_dim + j];
+                        for (int j = 0; j < (GRID_DD > 0 ? GRID_DD : -GRID_DD); ++j) xd[j] = out_d[row * p.desc_dim + j];
                         const int32_t cell = GRID_DD > 0 ? qdx_grid_cell<(GRID_DD > 0 ? GRID_DD : 1)>(xd, p.grid, s_axes, p.centroids, p.K)
                                                          : qdx_index_cell<(GRID_DD < 0 ? -GRID_DD : 1)>(xd, p.cvt);
                         if (p.out_cell) p.out_cell[row] = cell;
-                        if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins);
+                        if (p.offer && qdx_offer(p.ws, p.K, p.rep_f, cell, fit, p.idx_base + (uint32_t)row, p.first_wins) && p.store_mode == 1)
+                            qdx_store_row(out_g + row * D, xr, dc, p.out_xchg);
                     }
                 }
             }
         }
-        // the tile is rewritten by the next chunk: wait until the bulk engine has finished READING it
-        if (p.out_g) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        // the tile is rewritten by the next chunk / tile: wait until the bulk engine has finished READING it
+        if (out_g && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         __syncwarp();
+    }
+    }   // tiles of this warp
+    if (p.out_xchg) {
+        // peers read these rows straight out of this rank's memory once its arrival flag is up (qdx_xchg_cta_done): the
+        // bulk copies must have COMPLETED (not merely been read out of shared memory) and be visible at system scope
+        if (out_g && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+        __threadfence_system();
     }
 }
 
@@ -1111,13 +1077,32 @@ static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
     return 0;
 }
 
+// Grid of the generate kernel: ceil(B / 128) CTAs, capped at ONE resident wave (SMs x CTAs per SM for this instantiation and
+// this much dynamic shared memory): the kernel is persistent, warp w owns rows [B w / W, B (w + 1) / W).
+template <typename Kern>
+static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0, per_sm = 0;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QDX_GEN_WARPS * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return QDX_ERR_UNSUPPORTED;
+    int64_t g = (B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32);
+    const int64_t cap = (int64_t)sms * per_sm;
+    *grid_out = (unsigned)(g < cap ? g : cap);
+    return 0;
+}
+
 template <int TASK, bool ARM_CLIP>
-static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, cudaStream_t st) {
+static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t st) {
 #define QDX_LAUNCH_GEN(GD)                                                                                         \
     do {                                                                                                           \
-        cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<TASK, GD, ARM_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return (int)e;                                                                       \
-        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);                        \
+        unsigned g_ = 0;                                                                                           \
+        int rc_ = generate_grid(qdx_generate_kernel<TASK, GD, ARM_CLIP>, smem, p.B, &g_);                          \
+        if (rc_) return rc_;                                                                                       \
+        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(p);                          \
     } while (0)
     const int gd = (TASK == QDX_TASK_NONE) ? 0 : (p.grid.dd ? p.grid.dd : -p.cvt.dd);
     if (TASK == QDX_TASK_ARM) {            // arm descriptors are 2-D: grid 2, bucket index 2, or none
@@ -1129,9 +1114,10 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, dim3 grid, c
         }
     } else if (TASK == QDX_TASK_NONE) {
         if (p.leaves.n > 1) {
-            cudaError_t e = cudaFuncSetAttribute(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<grid, QDX_GEN_WARPS * 32, smem, st>>>(p);
+            unsigned g_ = 0;
+            int rc_ = generate_grid(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, smem, p.B, &g_);
+            if (rc_) return rc_;
+            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(p);
         } else {
             QDX_LAUNCH_GEN(0);
         }
@@ -1267,8 +1253,11 @@ static int generate_impl(const float* rep_genotypes, const float* rep_fitness, c
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
                  int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, const qdx_cvt_index* cvt,
-                 const qdx_leaf_table* leaves, void* stream) {
+                 const qdx_leaf_table* leaves, int32_t flags, void* stream) {
     if (!rep_genotypes || !rep_fitness || !ws || K <= 0 || D <= 0 || B < 0 || (D & 3)) return QDX_ERR_ARG;
+    if (flags & ~(QDX_GEN_ROWS_FIRED_ONLY | QDX_GEN_OUT_XCHG)) return QDX_ERR_ARG;
+    if ((flags & QDX_GEN_OUT_XCHG) && task == QDX_TASK_NONE) return QDX_ERR_ARG;
+    if (flags & QDX_GEN_OUT_XCHG) out_genotypes = (float*)16;      // placeholder: the rows go to this rank's offspring block, resolved on the device
     if (task < QDX_TASK_NONE || task > QDX_TASK_SPHERE) return QDX_ERR_ARG;
     if (task != QDX_TASK_NONE && (!out_fitness || !out_desc || desc_dim < 1 || desc_dim > D || desc_dim > 128)) return QDX_ERR_ARG;
     if (task == QDX_TASK_ARM && desc_dim != 2) return QDX_ERR_ARG;
@@ -1291,6 +1280,9 @@ static int generate_impl(const float* rep_genotypes, const float* rep_fitness, c
     p.DC = (D <= 128) ? (int32_t)D : 128;
     p.DS = ((p.DC & 7) == 4) ? p.DC : p.DC + 4;
     if (task == QDX_TASK_ARM && D > p.DC) return QDX_ERR_UNSUPPORTED;   // arm needs the whole row for its two passes
+    p.out_xchg = (flags & QDX_GEN_OUT_XCHG) ? 1 : 0;
+    // only the rows whose offer fired: needs the offer in this kernel and the whole row in the tile when the offer is made
+    p.store_mode = ((flags & QDX_GEN_ROWS_FIRED_ONLY) && offer && D <= p.DC) ? 1 : 0;
     p.iso_sigma = iso_sigma; p.line_sigma = line_sigma; p.has_min = has_min; p.has_max = has_max; p.minv = minval; p.maxv = maxval;
     p.out_g = out_genotypes; p.out_f = out_fitness; p.out_d = out_desc; p.out_cell = out_cells; p.out_p1 = out_p1; p.out_p2 = out_p2;
     p.desc_dim = desc_dim; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
@@ -1306,15 +1298,14 @@ static int generate_impl(const float* rep_genotypes, const float* rep_fitness, c
         if (p.leaves.n == 1) p.keys.leaf = p.leaves.key[0];
     }
     const size_t smem = ((size_t)QDX_GEN_WARPS * 32 * p.DS + (size_t)p.grid.total_axes) * sizeof(float);
-    const dim3 g((unsigned)((B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32)));
     // arm.py:27 clip(params, 0, 1) is the identity when the variation already clipped into [0, 1]
     const bool arm_clip = !(has_min && has_max && minval >= 0.0f && maxval <= 1.0f);
     switch (task) {
-        case QDX_TASK_NONE: return launch_generate_task<QDX_TASK_NONE, false>(p, smem, g, S(stream));
-        case QDX_TASK_ARM: return arm_clip ? launch_generate_task<QDX_TASK_ARM, true>(p, smem, g, S(stream))
-                                           : launch_generate_task<QDX_TASK_ARM, false>(p, smem, g, S(stream));
-        case QDX_TASK_RASTRIGIN: return launch_generate_task<QDX_TASK_RASTRIGIN, false>(p, smem, g, S(stream));
-        default: return launch_generate_task<QDX_TASK_SPHERE, false>(p, smem, g, S(stream));
+        case QDX_TASK_NONE: return launch_generate_task<QDX_TASK_NONE, false>(p, smem, S(stream));
+        case QDX_TASK_ARM: return arm_clip ? launch_generate_task<QDX_TASK_ARM, true>(p, smem, S(stream))
+                                           : launch_generate_task<QDX_TASK_ARM, false>(p, smem, S(stream));
+        case QDX_TASK_RASTRIGIN: return launch_generate_task<QDX_TASK_RASTRIGIN, false>(p, smem, S(stream));
+        default: return launch_generate_task<QDX_TASK_SPHERE, false>(p, smem, S(stream));
     }
 }
 
@@ -1417,19 +1408,20 @@ int qdx_elect_winners(void* ws, int64_t K, int64_t D, int32_t task, int32_t desc
 }
 
 // ---- peer-memory exchange buffers (cudaMalloc + cudaIpc: one process per GPU, one NVLink / NVSwitch domain) ----
-int qdx_xchg_bytes(int64_t K, int64_t* bytes) {
-    if (K <= 0 || K >= (1ll << 31) || !bytes) return QDX_ERR_ARG;
-    *bytes = (int64_t)qdx_xchg_total_bytes(K);
+int qdx_xchg_bytes(int64_t K, int64_t B_dev, int64_t D, int32_t desc_dim, int64_t* bytes) {
+    if (K <= 0 || K >= (1ll << 31) || B_dev < 0 || !bytes || (B_dev > 0 && (D <= 0 || desc_dim < 1))) return QDX_ERR_ARG;
+    *bytes = (int64_t)qdx_xchg_total_bytes(K, B_dev, D, desc_dim);
     return 0;
 }
 
-int qdx_xchg_create(int64_t K, void** buf, void* ipc_handle64) {
-    if (K <= 0 || K >= (1ll << 31) || !buf || !ipc_handle64) return QDX_ERR_ARG;
+int qdx_xchg_create(int64_t K, int64_t B_dev, int64_t D, int32_t desc_dim, void** buf, void* ipc_handle64) {
+    if (K <= 0 || K >= (1ll << 31) || B_dev < 0 || !buf || !ipc_handle64 || (B_dev > 0 && (D <= 0 || desc_dim < 1))) return QDX_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, qdx_xchg_total_bytes(K));
+    const size_t n = qdx_xchg_total_bytes(K, B_dev, D, desc_dim);
+    cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemset(p, 0, qdx_xchg_total_bytes(K));
+    e = cudaMemset(p, 0, n);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle64, p);
     if (e != cudaSuccess) { cudaFree(p); return (int)e; }
@@ -1447,13 +1439,15 @@ int qdx_xchg_open(const void* ipc_handle64, void** peer_buf) {
 int qdx_xchg_close(void* peer_buf) { return peer_buf ? (int)cudaIpcCloseMemHandle(peer_buf) : QDX_ERR_ARG; }
 int qdx_xchg_destroy(void* buf) { return buf ? (int)cudaFree(buf) : QDX_ERR_ARG; }
 
-int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, void* stream) {
+int qdx_xchg_attach(void* ws, int32_t rank, int32_t nranks, void* const* bufs, int64_t B_dev, int64_t D, int32_t desc_dim,
+                    int32_t timeout_ms, void* stream) {
     if (!ws || nranks < 0 || nranks > QDX_MAX_PEERS || (nranks > 0 && (!bufs || rank < 0 || rank >= nranks))) return QDX_ERR_ARG;
-    struct { uint32_t push_ticket, pad0; unsigned long long peer[QDX_MAX_PEERS]; int32_t rank, nranks; } h;
-    static_assert(offsetof(QdxWorkspace, xchg_nranks) - offsetof(QdxWorkspace, push_ticket) + sizeof(int32_t) == sizeof(h), "layout");
+    if (B_dev < 0 || (B_dev > 0 && (D <= 0 || desc_dim < 1))) return QDX_ERR_ARG;
+    struct { uint32_t push_ticket, pad0; unsigned long long peer[QDX_MAX_PEERS]; int32_t rank, nranks; int64_t bdev; int32_t D, Dd, timeout_ms, pad1; } h;
+    static_assert(offsetof(QdxWorkspace, pad1) - offsetof(QdxWorkspace, push_ticket) + sizeof(int32_t) == sizeof(h), "layout");
     memset(&h, 0, sizeof(h));
     for (int q = 0; q < nranks; ++q) { if (!bufs[q]) return QDX_ERR_ARG; h.peer[q] = (unsigned long long)bufs[q]; }
-    h.rank = rank; h.nranks = nranks;
+    h.rank = rank; h.nranks = nranks; h.bdev = nranks > 0 ? B_dev : 0; h.D = (int32_t)D; h.Dd = desc_dim; h.timeout_ms = timeout_ms;
     return (int)cudaMemcpyAsync((char*)ws + offsetof(QdxWorkspace, push_ticket), &h, sizeof(h), cudaMemcpyHostToDevice, S(stream));
 }
 
@@ -1473,10 +1467,10 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
                  float maxval, int32_t task, int32_t desc_dim, const qdx_grid_desc* grid, int32_t offer,
                  uint32_t idx_base, int32_t first_wins, float* out_genotypes, float* out_fitness, float* out_desc,
                  int32_t* out_cells, int32_t* out_p1, int32_t* out_p2, const uint32_t* gen_keys8, const qdx_cvt_index* cvt,
-                 void* stream) {
+                 int32_t flags, void* stream) {
     return generate_impl(rep_genotypes, rep_fitness, centroids, ws, K, D, B, iso_sigma, line_sigma, has_min, minval, has_max, maxval,
                          task, desc_dim, grid, offer, idx_base, first_wins, out_genotypes, out_fitness, out_desc, out_cells, out_p1,
-                         out_p2, gen_keys8, cvt, nullptr, stream);
+                         out_p2, gen_keys8, cvt, nullptr, flags, stream);
 }
 
 int qdx_generate_leaves(const float* rep_genotypes, const float* rep_fitness, void* ws, int64_t K, int64_t D, int64_t B,
@@ -1486,7 +1480,7 @@ int qdx_generate_leaves(const float* rep_genotypes, const float* rep_fitness, vo
     if (!leaves || !gen_keys8) return QDX_ERR_ARG;
     return generate_impl(rep_genotypes, rep_fitness, nullptr, ws, K, D, B, iso_sigma, line_sigma, has_min, minval, has_max, maxval,
                          QDX_TASK_NONE, 1, nullptr, 0, 0u, 1, out_genotypes, nullptr, nullptr, nullptr, out_p1, out_p2, gen_keys8,
-                         nullptr, leaves, stream);
+                         nullptr, leaves, 0, stream);
 }
 
 int qdx_isoline_variation_leaves(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t line_k0, uint32_t line_k1,

@@ -10,21 +10,23 @@
 extern "C" int qdx_map_elites_step(const qdx_step_desc* s, int32_t key_mode, uint32_t k0, uint32_t k1, uint32_t* carry_io2,
                                    float* metrics_out4, void* stream) {
     if (!s || !s->rep_genotypes || !s->rep_fitness || !s->rep_desc || !s->centroids || !s->ws) return QDX_ERR_ARG;
-    if (!s->off_genotypes || !s->off_fitness || !s->off_desc || !s->off_cells) return QDX_ERR_ARG;
     if (s->nranks < 1 || s->rank < 0 || s->rank >= s->nranks) return QDX_ERR_ARG;
-    if (s->nranks > 1 && (s->exchange != QDX_EXCHANGE_P2P || !s->stage_genotypes || !s->stage_fitness || !s->stage_desc)) return QDX_ERR_ARG;
+    const bool multi = s->nranks > 1;
+    if (multi && s->exchange != QDX_EXCHANGE_P2P) return QDX_ERR_ARG;
+    if (!s->off_cells || !s->off_fitness || !s->off_desc || (!multi && !s->off_genotypes)) return QDX_ERR_ARG;
     uint32_t keys[8];
     int rc = qdx_host_generation_keys(key_mode, k0, k1, carry_io2, keys);
     if (rc) return rc;
     const bool grid = s->grid && s->grid->dd != 0;
     const bool index = !grid && s->cvt && s->cvt->dd != 0;
     const bool fused_cells = grid || index;
-    const bool multi = s->nranks > 1;
     const uint32_t base = (uint32_t)((int64_t)s->rank * s->B);
+    // only the rows that can be elected are written (fused offer); multi-GPU: into this rank's offspring block, where the peers read them
+    const int32_t flags = QDX_GEN_ROWS_FIRED_ONLY | (multi ? QDX_GEN_OUT_XCHG : 0);
     rc = qdx_generate(s->rep_genotypes, s->rep_fitness, s->centroids, s->ws, s->K, s->D, s->B, s->iso_sigma, s->line_sigma, s->has_min,
                       s->minval, s->has_max, s->maxval, s->task, s->desc_dim, grid ? s->grid : nullptr, fused_cells ? 1 : 0, base,
                       s->first_wins, s->off_genotypes, s->off_fitness, s->off_desc, s->off_cells, nullptr, nullptr, keys,
-                      index ? s->cvt : nullptr, stream);
+                      index ? s->cvt : nullptr, flags, stream);
     if (rc) return rc;
     if (!fused_cells) {     // cell assignment stays sharded with the offspring: tensor-core pass or FP32 brute force, + offer
         if (s->tc_prep && s->tc_scratch)
@@ -36,13 +38,6 @@ extern "C" int qdx_map_elites_step(const qdx_step_desc* s, int32_t key_mode, uin
         if (rc) return rc;
         if (multi) { rc = qdx_xchg_push(s->ws, s->K, keys, stream); if (rc) return rc; }
     }
-    if (!multi)
-        return qdx_commit(s->ws, s->K, s->D, s->desc_dim, s->off_genotypes, s->off_fitness, s->off_desc, base, s->B, s->first_wins,
-                          s->rep_genotypes, s->rep_fitness, s->rep_desc, s->qd_offset, metrics_out4, nullptr, 0, stream);
-    rc = qdx_elect_winners(s->ws, s->K, s->D, s->task, s->desc_dim, s->B, s->nranks, s->rep_genotypes, s->iso_sigma, s->line_sigma,
-                           s->has_min, s->minval, s->has_max, s->maxval, s->first_wins, s->stage_genotypes, s->stage_fitness,
-                           s->stage_desc, s->peer_timeout_ms > 0 ? s->peer_timeout_ms : 30000, stream);
-    if (rc) return rc;
-    return qdx_commit(s->ws, s->K, s->D, s->desc_dim, s->stage_genotypes, s->stage_fitness, s->stage_desc, 0u, s->K, s->first_wins,
-                      s->rep_genotypes, s->rep_fitness, s->rep_desc, s->qd_offset, metrics_out4, nullptr, 2, stream);
+    return qdx_commit(s->ws, s->K, s->D, s->desc_dim, s->off_genotypes, s->off_fitness, s->off_desc, base, s->B, s->first_wins,
+                      s->rep_genotypes, s->rep_fitness, s->rep_desc, s->qd_offset, metrics_out4, nullptr, multi ? 3 : 0, stream);
 }

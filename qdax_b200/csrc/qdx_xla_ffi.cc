@@ -114,7 +114,8 @@ ffi::Error ScanUpdateImpl(cudaStream_t stream, int64_t batch, int32_t task, floa
     if (rc) return Status("qdx_select_prepare", rc);
     rc = qdx_generate(out_g->typed_data(), out_f->typed_data(), centroids.typed_data(), w, K, D, batch, iso_sigma, line_sigma, has_min,
                       minval, has_max, maxval, task, /*desc_dim=*/2, &grid, /*offer=*/1, 0u, first_wins, off_g->typed_data(),
-                      off_f->typed_data(), off_d->typed_data(), nullptr, nullptr, nullptr, /*gen_keys8=*/nullptr, /*cvt=*/nullptr, stream);
+                      off_f->typed_data(), off_d->typed_data(), nullptr, nullptr, nullptr, /*gen_keys8=*/nullptr, /*cvt=*/nullptr,
+                      /*flags=*/QDX_GEN_ROWS_FIRED_ONLY, stream);
     if (rc) return Status("qdx_generate", rc);
     rc = qdx_commit(w, K, D, 2, off_g->typed_data(), off_f->typed_data(), off_d->typed_data(), 0u, batch, first_wins, out_g->typed_data(),
                     out_f->typed_data(), out_d->typed_data(), qd_offset, metrics->typed_data(), nullptr, 0, stream);
