@@ -109,6 +109,11 @@ int qdx_generate(const float* rep_genotypes, const float* rep_fitness, const flo
 int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_t desc_dim, float* out_fitness,
               float* out_desc, void* stream);
 
+/* noisy_arm_scoring_function (qdax/tasks/arm.py:53-81): (k0, k1) = the key handed to the scoring function; Gaussian noise on
+ * the genotype before the arm is evaluated, on the fitness and on the descriptor afterwards. */
+int qdx_score_noisy_arm(const float* genotypes, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float fit_variance, float desc_variance,
+                        float params_variance, float* out_fitness, float* out_desc, void* stream);
+
 /* ---- stage (c): get_cells_indices (mapelites_repertoire.py:111-137); grid == NULL or grid->dd == 0: brute
  * force with first-index argmin.  offer != 0 additionally performs the per-cell best-offspring offer. */
 int qdx_cells(const float* desc, int64_t B, int32_t desc_dim, const float* centroids, int64_t K, const qdx_grid_desc* grid,
@@ -269,6 +274,28 @@ int qdx_mels_offer(const int32_t* cells_all, const float* desc_all, const float*
 /* dst[c, :] = src[source_of_cell[c], :] where source_of_cell[c] >= 0 (qdx_commit's added_cells): per-cell side arrays
  * (spreads, extra_scores; mapelites_repertoire.py:250-257) */
 int qdx_scatter_rows_by_source(const int32_t* source_of_cell, const float* src, int64_t K, int64_t W, float* dst, void* stream);
+
+/* MOMERepertoire.add (qdax/core/containers/mome_repertoire.py:211-322): the batch is scanned in index order, every offspring
+ * updating the Pareto front of its cell (_update_masked_pareto_front :72-209, masked dominance of qdax/utils/pareto_front.py:
+ * 48-95), in place.  rep_fitness (K, front_len, num_criteria) with -inf rows for empty slots, rep_genotypes (K, front_len, D),
+ * rep_desc (K, front_len, desc_dim); cells = qdx_cells of the batch descriptors.  One warp per cell (offspring of one cell are
+ * applied sequentially, cells in parallel).  front_len <= 256, num_criteria <= 8.  ieee_literal: how the source's float * bool
+ * products are read -- 0: XLA's compiled Select(mask, x, 0) (default), 1: IEEE product of the converted mask (inf * 0 = NaN). */
+int qdx_mome_add(float* rep_fitness, float* rep_genotypes, float* rep_desc, int64_t K, int32_t front_len, int32_t num_criteria, int64_t D,
+                 int32_t desc_dim, const int32_t* cells, const float* fitness, const float* genotypes, const float* desc, int64_t B,
+                 int32_t ieee_literal, void* stream);
+/* UnstructuredRepertoire.add (qdax/core/containers/unstructured_repertoire.py:162-337) in three calls around two gathers:
+ * qdx_unstructured_plan: nearest / second-nearest occupied slot as the source computes them (see oracle/
+ * qdax_containers_numpy.py), the l-value tests, the re-ordering of the batch (offspring that open a new slot first) ->
+ * out_order (B int32: position -> batch index; `scratch` keeps the target slots and flags).  The caller gathers genotypes /
+ * descriptors / fitnesses by out_order (qdx_gather_rows), then qdx_unstructured_offer runs intra_batch_comp (:69-129) and the
+ * segment_max election into the workspace key table (N = max_size cells), and qdx_commit(off_* = the gathered batch) applies it.
+ * qdx_unstructured_scratch: bytes of `scratch`. */
+int qdx_unstructured_scratch(int64_t N, int64_t B, int64_t* bytes);
+int qdx_unstructured_plan(const float* rep_fitness, const float* rep_desc, int64_t N, int32_t desc_dim, const float* fitness, const float* desc,
+                          int64_t B, float l_value, void* scratch, int32_t* out_order, void* stream);
+int qdx_unstructured_offer(const float* sorted_fitness, const float* sorted_desc, int64_t B, int32_t desc_dim, int64_t N, float l_value,
+                           void* scratch, const int32_t* order, void* ws, const float* rep_fitness, int32_t first_wins, void* stream);
 
 /* ---- compute_cvt_centroids on the GPU (mapelites_repertoire.py:30-72 calls scikit-learn KMeans on
  * the host).  One Lloyd iteration = qdx_cells (assignment) + qdx_kmeans_accumulate + qdx_kmeans_update.  The update is

@@ -196,6 +196,17 @@ def score(task: str, g, desc_dim: int = 2):
     return f, d
 
 
+def noisy_arm(g, key, fit_variance: float, desc_variance: float, params_variance: float):
+    """noisy_arm_scoring_function (qdax/tasks/arm.py:53-81) with the exact arithmetic."""
+    g = _f(g)
+    B, D = g.shape
+    f = np.zeros(B, dtype=F32)
+    d = np.zeros((B, 2), dtype=F32)
+    _chk(lib().qo_noisy_arm(_p(g), C.c_int64(B), C.c_int64(D), _p(_key(key)), C.c_float(fit_variance), C.c_float(desc_variance),
+                            C.c_float(params_variance), _p(f), _p(d)), "noisy_arm")
+    return f, d
+
+
 def cells(desc, centroids) -> np.ndarray:
     desc, centroids = _f(desc), _f(centroids)
     B, Dd = desc.shape

@@ -412,6 +412,22 @@ def arm_scoring_function(params: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return (-f).astype(F32), np.stack([xs, ys], axis=-1).astype(F32)
 
 
+def noisy_arm_scoring_function(params: np.ndarray, key, fit_variance: float, desc_variance: float,
+                               params_variance: float) -> Tuple[np.ndarray, np.ndarray]:
+    """qdax/tasks/arm.py:53-81: key, f_sub, d_sub, p_sub = split(key, 4); params += normal(p_sub) * params_variance; arm;
+    fitnesses += normal(f_sub) * fit_variance; descriptors += normal(d_sub) * desc_variance."""
+    from . import jax_prng as jr
+
+    p = np.asarray(params, dtype=F32)
+    ks = jr.split(np.asarray(key, dtype=np.uint32), 4)                                   # :65
+    f_sub, d_sub, p_sub = ks[1], ks[2], ks[3]
+    noisy = (p + (jr.normal(p_sub, p.shape) * F32(params_variance)).astype(F32)).astype(F32)   # :68
+    f, d = arm_scoring_function(noisy)                                                   # :71
+    f = (f + (jr.normal(f_sub, f.shape) * F32(fit_variance)).astype(F32)).astype(F32)    # :74-76
+    d = (d + (jr.normal(d_sub, d.shape) * F32(desc_variance)).astype(F32)).astype(F32)   # :77-80
+    return f, d
+
+
 def rastrigin_scoring_function(params: np.ndarray, desc_dim: int = 2) -> Tuple[np.ndarray, np.ndarray]:
     p = np.asarray(params, dtype=F32)
     D = p.shape[-1]

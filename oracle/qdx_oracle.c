@@ -563,6 +563,37 @@ QO_API int qo_score(int task, const float* g, int64_t B, int64_t D, int64_t Dd, 
     return 0;
 }
 
+/* noisy_arm_scoring_function -- qdax/tasks/arm.py:53-81: key, f_sub, d_sub, p_sub = split(key, 4); the genotype gets
+ * normal(p_sub, params.shape) * params_variance added before the arm is evaluated, the fitness normal(f_sub, (B,)) *
+ * fit_variance and the descriptor normal(d_sub, (B, 2)) * desc_variance afterwards (one rounding per operation). */
+QO_API int qo_noisy_arm(const float* g, int64_t B, int64_t D, const uint32_t* key, float fit_variance, float desc_variance,
+                        float params_variance, float* f, float* desc) {
+    qo_key k = {key[0], key[1]};
+    const qo_key kf = split_i(k, 1), kd = split_i(k, 2), kp = split_i(k, 3);
+#pragma omp parallel
+    {
+        float* row = (float*)malloc(sizeof(float) * (size_t)D);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < B; ++i) {
+            for (int64_t d = 0; d < D; ++d) {
+                float n = normal_from_bits(bits32(kp, (uint64_t)(i * D + d)));
+                float t = n * params_variance;
+                row[d] = g[i * D + d] + t;
+            }
+            float fi, di[2];
+            score_row(0, row, D, 2, &fi, di);
+            float nf = normal_from_bits(bits32(kf, (uint64_t)i)) * fit_variance;
+            f[i] = fi + nf;
+            for (int j = 0; j < 2; ++j) {
+                float nd = normal_from_bits(bits32(kd, (uint64_t)(2 * i + j))) * desc_variance;
+                desc[2 * i + j] = di[j] + nd;
+            }
+        }
+        free(row);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ cell assignment
  * get_cells_indices -- qdax/core/containers/mapelites_repertoire.py:111-137: brute force,
  * argmin_k sum_d (x_d - c_kd)^2 (sequential over d), first minimum, NaN counts as minimal. */

@@ -114,6 +114,7 @@ PROTOTYPES = {
     "qdx_host_split": [_u32, _u32, _i32, _vp],
     "qdx_host_generation_keys": [_i32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)],
     "qdx_score": [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp],
+    "qdx_score_noisy_arm": [_vp, _i64, _i64, _u32, _u32, _f32, _f32, _f32, _vp, _vp, _vp],
     "qdx_cells": [_vp, _i64, _i32, _vp, _i64, C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i32, _u32, _i32, _vp],
     "qdx_cvt_index_plan": [_vp, _i64, _i32, C.POINTER(CvtIndexDesc), C.POINTER(_i64)],
     "qdx_cvt_index_build": [_vp, _i64, C.POINTER(CvtIndexDesc), _vp, _vp, _vp],
@@ -131,6 +132,10 @@ PROTOTYPES = {
     "qdx_isoline_variation_leaves": [_vp, _vp, _i64, _i64, _u32, _u32, C.POINTER(LeafTable), _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp],
     "qdx_copy_2d": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
     "qdx_mels_offer": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp],
+    "qdx_mome_add": [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "qdx_unstructured_scratch": [_i64, _i64, C.POINTER(_i64)],
+    "qdx_unstructured_plan": [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _f32, _vp, _vp, _vp],
+    "qdx_unstructured_offer": [_vp, _vp, _i64, _i32, _i64, _f32, _vp, _vp, _vp, _vp, _i32, _vp],
     "qdx_scatter_rows_by_source": [_vp, _vp, _i64, _i64, _vp, _vp],
     "qdx_kmeans_accumulate": [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp],
     "qdx_kmeans_update": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
@@ -165,7 +170,7 @@ def lib() -> C.CDLL:
 
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
-KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_generate_leaves": 1, "qdx_isoline_variation_leaves": 1, "qdx_copy_2d": 1, "qdx_kmeans_accumulate": 1, "qdx_kmeans_update": 1, "qdx_mels_offer": 1, "qdx_scatter_rows_by_source": 1, "qdx_score": 1, "qdx_cells": 1, "qdx_cells_indexed": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
+KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_generate_leaves": 1, "qdx_isoline_variation_leaves": 1, "qdx_copy_2d": 1, "qdx_kmeans_accumulate": 1, "qdx_kmeans_update": 1, "qdx_mels_offer": 1, "qdx_mome_add": 1, "qdx_unstructured_plan": 3, "qdx_unstructured_offer": 3, "qdx_scatter_rows_by_source": 1, "qdx_score": 1, "qdx_score_noisy_arm": 1, "qdx_cells": 1, "qdx_cells_indexed": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
                    "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0

@@ -466,6 +466,17 @@ def score(task: str, g: torch.Tensor, desc_dim: int = 2, out_f: Optional[torch.T
     return f, d
 
 
+def score_noisy_arm(g: torch.Tensor, key, fit_variance: float, desc_variance: float, params_variance: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    g = require_cuda(g, "genotypes")
+    B, D = g.shape
+    k0, k1 = key_words(key)
+    f = torch.empty(B, dtype=torch.float32, device=g.device)
+    d = torch.empty(B, 2, dtype=torch.float32, device=g.device)
+    call("qdx_score_noisy_arm", _ptr(g), C.c_int64(B), C.c_int64(D), C.c_uint32(k0), C.c_uint32(k1), C.c_float(fit_variance),
+         C.c_float(desc_variance), C.c_float(params_variance), _ptr(f), _ptr(d), _stream())
+    return f, d
+
+
 TC_MIN_DIM, TC_MAX_DIM, TC_MIN_CENTROIDS = 8, 32, 1024     # where the tensor-core pass pays off
 
 

@@ -81,6 +81,9 @@ struct QdxWorkspace {
     uint32_t cta_arrived;   // grid barrier of the streaming commit (reset by its last CTA)
     uint32_t job_count;     // entries of the global list of changed cells (reset by the last CTA)
     uint32_t job_next;      // next batch of the list handed out to a streaming warp (reset by the last CTA)
+    // generate kernel (persistent grid): next offspring row to hand out, CTAs done (both reset by the last CTA to finish)
+    uint32_t gen_next_row;
+    uint32_t gen_done;
 };
 
 // Raise the sticky device error flag (first error wins on the host mirror: later ones only overwrite the device copy).
@@ -317,21 +320,4 @@ QDX_DEV void qdx_xchg_publish(QdxWorkspace* ws, int64_t K, const QdxGenKeys& key
     }
     __threadfence_system();
     for (int q = 0; q < R; ++q) qdx_st_release_sys((unsigned long long*)ws->xchg_peer[q] + me, (unsigned long long)(epoch + 1u));
-}
-// Called by one thread of every CTA of an offering kernel when the CTA is done (after __syncthreads; every thread that
-// pushed a record has already fenced at system scope): the last CTA of the grid publishes.
-QDX_DEV void qdx_xchg_cta_done(void* ws_raw, int64_t K, const QdxGenKeys& keys, unsigned total_ctas) {
-    QdxWorkspace* ws = (QdxWorkspace*)ws_raw;
-    if (ws->xchg_nranks <= 0) return;
-    __threadfence();
-    if (atomicAdd(&ws->push_ticket, 1u) == total_ctas - 1u) {
-        ws->push_ticket = 0u;
-#if QDX_XCHG_TRACE
-        const unsigned long long t0 = qdx_now();
-#endif
-        qdx_xchg_publish(ws, K, keys);
-#if QDX_XCHG_TRACE
-        atomicAdd(&g_xchg_trace[3], 1ull); atomicAdd(&g_xchg_trace[4], qdx_now() - t0);
-#endif
-    }
 }

@@ -134,6 +134,7 @@ struct QdxGenParams {
     QdxGrid grid;
     int32_t offer; uint32_t idx_base; int32_t first_wins;
     int32_t keys_by_value; QdxGenKeys keys;          // generation keys derived on the host (qdx_host_generation_keys)
+    int32_t tile_rows;                                // rows per tile handed to a warp (<= 32): the batch is a whole number of tiles per warp
     int32_t store_mode;                               // 0: every offspring row (bulk copy of the tile); 1: only the rows whose offer fired
     int32_t out_xchg;                                 // 1: out_g / out_f / out_d = this rank's offspring block of the exchange buffer (epoch parity)
     QdxCvtIndex cvt;                                  // bucket index over non-grid centroids (GRID_DD < 0)
@@ -182,11 +183,18 @@ __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(con
     __syncthreads();
     QDX_GEN_STAMP(2, atomicMin); QDX_GEN_STAMP(3, atomicMax);
 #endif
-    // multi-GPU peer-memory exchange: this CTA's offers (and their pushes into the peers) are done; the last CTA of
-    // the grid publishes this rank's generation keys and raises its arrival flag in every peer
-    if (GRID_DD != 0 && p.offer && p.keys_by_value) {
-        __syncthreads();
-        if (threadIdx.x == 0) qdx_xchg_cta_done(p.ws, p.K, p.keys, gridDim.x);
+    // the last CTA of the grid to finish re-arms the row counter for the next launch; multi-GPU peer-memory exchange: this
+    // CTA's offers (and their pushes into the peers) are done, the last CTA also publishes this rank's generation keys and
+    // raises its arrival flag in every peer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        QdxWorkspace* ws = (QdxWorkspace*)p.ws;
+        const bool publish = GRID_DD != 0 && p.offer && p.keys_by_value && ws->xchg_nranks > 0;
+        __threadfence();
+        if (atomicAdd(&ws->gen_done, 1u) == gridDim.x - 1u) {
+            ws->gen_done = 0u; ws->gen_next_row = 0u;
+            if (publish) { __threadfence(); qdx_xchg_publish(ws, p.K, p.keys); }
+        }
     }
 }
 
@@ -210,12 +218,15 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
     }
 
     float* tile = s_tiles + (size_t)warp * 32 * DS;
-    // Persistent grid (at most one resident wave of CTAs): warp w of the grid owns the contiguous rows
-    // [B w / W, B (w + 1) / W) and walks them in tiles of up to 32 rows, so every warp of every SM has work until the very
-    // end of the kernel whatever B is (a grid of ceil(B / 128) CTAs left the SMs 27 % idle during the second "wave" of the
-    // 131 072-row shards of an 8-GPU run), and the per-CTA prologue above is paid once.
-    const int64_t n_warps = (int64_t)gridDim.x * QDX_GEN_WARPS, w_id = (int64_t)blockIdx.x * QDX_GEN_WARPS + warp;
-    const int64_t r_lo = p.B * w_id / n_warps, r_hi = p.B * (w_id + 1) / n_warps;
+    // Persistent grid (at most one resident wave of CTAs), rows handed out to the WARPS from a grid-wide counter in tiles of
+    // p.tile_rows <= 32 rows.  The tile height is chosen by the launcher so that the batch is a whole number of tiles per warp
+    // (131 072 rows over 2368 warps = 55.4 rows each = two tiles of 28): with ceil(B / 128) CTAs of one 32-row tile per warp
+    // the second, partial wave of such a shard (8-GPU run) ran with 27 % of the SMs' warp slots empty.  The deal must be
+    // dynamic: co-resident warps do not progress at the same rate (the issue arbiter is priority-based), a static split left
+    // SMs half empty for the last third of the kernel (first CTA done at 442 us, last at 737 us for 2^20 rows).  A finer
+    // guided deal (tiles shrinking to 8 rows) lost more to the per-tile cost of the row-serial scoring phase than it gained.
+    // Results do not depend on who processes which row: the random streams are counter-based on the row index.
+    QdxWorkspace* wsm = (QdxWorkspace*)p.ws;
     const QdxGenKeys keys = p.keys_by_value ? p.keys : ws->keys;
     const int32_t* __restrict__ occ = qdx_ws_occ(p.ws);
     const float total = ws->sel.total;
@@ -225,9 +236,15 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         const QdxOffBlock ob = qdx_xchg_block(p.ws, p.K, ws->xchg_rank, qdx_xchg_parity(p.ws));      // fitness / descriptors to both places
         out_g = ob.g; xf = ob.f; xd = ob.d;
     }
-    for (int64_t row0 = r_lo; row0 < r_hi; row0 += 32) {
+    const uint32_t take = (uint32_t)p.tile_rows;
+    for (;;) {
+    uint32_t r0 = 0u;
+    if (lane == 0) r0 = atomicAdd(&wsm->gen_next_row, take);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    if ((int64_t)r0 >= p.B) break;
+    const int64_t row0 = (int64_t)r0;
     const int64_t row = row0 + lane;
-    const int nrows = (r_hi - row0) < 32 ? (int)(r_hi - row0) : 32;
+    const int nrows = (p.B - row0) < (int64_t)take ? (int)(p.B - row0) : (int)take;
     const bool valid = lane < nrows;
 
     // ---- phase 0: parents + line noise, lane = row --------------------------------------------------
@@ -429,9 +446,12 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
 // =====================================================================================================
 // standalone scoring:  (B, D) genotypes -> fitness (B,), descriptors (B, Dd)
 // =====================================================================================================
-template <int TASK>
+// NOISY (arm only): noisy_arm_scoring_function (qdax/tasks/arm.py:53-81) -- normal(p_sub, params.shape) * params_variance is
+// added while the rows are staged, normal(f_sub) * fit_variance / normal(d_sub) * desc_variance to the results.
+struct QdxNoise { QdxKey kf, kd, kp; float fit_var, desc_var, params_var; };
+template <int TASK, bool NOISY = false>
 __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict__ g, int64_t B, int32_t D, int32_t desc_dim,
-                                                        float* __restrict__ out_f, float* __restrict__ out_d) {
+                                                        float* __restrict__ out_f, float* __restrict__ out_d, const QdxNoise nz) {
     // One warp per 32-row tile; genotype chunks are staged row-major in shared memory with a coalesced
     // cooperative copy, then consumed row-serially (lane = row) in the canonical left-to-right order.
     extern __shared__ __align__(128) float s_tiles[];
@@ -451,7 +471,12 @@ __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict_
             __syncwarp();
             for (int i = lane; i < nrows * dc; i += 32) {       // coalesced: consecutive lanes -> consecutive genes
                 const int r = i / dc, d = i - r * dc;
-                tile[r * (DC + 1) + d] = g[(row0 + r) * D + d0 + d];
+                float v = g[(row0 + r) * D + d0 + d];
+                if (NOISY) {
+                    const float t = qdx_normal_from_bits(qdx_bits32(nz.kp, (uint64_t)(row0 + r) * (uint64_t)D + (uint64_t)(d0 + d))) * nz.params_var;
+                    v = v + t;
+                }
+                tile[r * (DC + 1) + d] = v;
             }
             __syncwarp();
             if (!valid) continue;
@@ -486,9 +511,17 @@ __global__ void __launch_bounds__(128) qdx_score_kernel(const float* __restrict_
     }
     if (!valid) return;
     if (TASK == QDX_TASK_ARM) {
-        out_f[row] = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
-        out_d[row * 2 + 0] = __fdiv_rn(cs, (float)(2 * D)) + 0.5f;
-        out_d[row * 2 + 1] = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
+        float f = -__fsqrt_rn(__fdiv_rn(sq, (float)D));
+        float dx = __fdiv_rn(cs, (float)(2 * D)) + 0.5f, dy = __fdiv_rn(sn, (float)(2 * D)) + 0.5f;
+        if (NOISY) {
+            const float nf = qdx_normal_from_bits(qdx_bits32(nz.kf, (uint64_t)row)) * nz.fit_var;
+            const float nx = qdx_normal_from_bits(qdx_bits32(nz.kd, 2ull * (uint64_t)row)) * nz.desc_var;
+            const float ny = qdx_normal_from_bits(qdx_bits32(nz.kd, 2ull * (uint64_t)row + 1ull)) * nz.desc_var;
+            f = f + nf; dx = dx + nx; dy = dy + ny;
+        }
+        out_f[row] = f;
+        out_d[row * 2 + 0] = dx;
+        out_d[row * 2 + 1] = dy;
     } else {
         float f = acc;
         if (TASK == QDX_TASK_RASTRIGIN) f = (float)(10.0 * (double)D) + f;
@@ -1081,18 +1114,44 @@ static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
 // this much dynamic shared memory): the kernel is persistent, warp w owns rows [B w / W, B (w + 1) / W).
 template <typename Kern>
 static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // (kernel, shared memory, device) -> resident CTAs: queried once, then served from a small table (the attribute call and
+    // the occupancy query cost microseconds each, on a path that enqueues a 100 us generation)
+    struct Entry { const void* k; size_t smem; int dev; int64_t cap; };
+    static Entry table[128];
+    static int n_entries = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 0, per_sm = 0;
-    e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QDX_GEN_WARPS * 32, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return QDX_ERR_UNSUPPORTED;
-    int64_t g = (B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32);
-    const int64_t cap = (int64_t)sms * per_sm;
+    int64_t cap = 0;
+    size_t limit = 0;                               // largest dynamic shared memory size this kernel has been opted in for (never lowered)
+    for (int i = 0; i < n_entries; ++i)
+        if (table[i].k == (const void*)kern && table[i].dev == dev) {
+            if (table[i].smem > limit) limit = table[i].smem;
+            if (table[i].smem == smem) cap = table[i].cap;
+        }
+    if (cap == 0) {
+        int sms = 0, per_sm = 0;
+        if (smem > limit || n_entries >= 128) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > limit ? smem : limit));
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QDX_GEN_WARPS * 32, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return QDX_ERR_UNSUPPORTED;
+        cap = (int64_t)sms * per_sm;
+        if (n_entries < 128) table[n_entries++] = Entry{(const void*)kern, smem, dev, cap};     // (a benign race: worst case an entry is queried twice)
+    }
+    const int64_t g = (B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32);
     *grid_out = (unsigned)(g < cap ? g : cap);
     return 0;
+}
+
+// Tile height: the rows of one warp (B / warps of the grid) cut into the fewest tiles of at most 32 rows, all the same size.
+static int32_t generate_tile_rows(int64_t B, unsigned ctas) {
+    const int64_t warps = (int64_t)ctas * QDX_GEN_WARPS;
+    const int64_t per_warp = (B + warps - 1) / warps;                   // ceil
+    if (per_warp <= 32) return 32;                                       // at most one tile per warp: full tiles
+    const int64_t tiles = (per_warp + 31) / 32;
+    const int64_t rows = (per_warp + tiles - 1) / tiles;
+    return (int32_t)(rows < 8 ? 8 : rows);
 }
 
 template <int TASK, bool ARM_CLIP>
@@ -1102,7 +1161,8 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
         unsigned g_ = 0;                                                                                           \
         int rc_ = generate_grid(qdx_generate_kernel<TASK, GD, ARM_CLIP>, smem, p.B, &g_);                          \
         if (rc_) return rc_;                                                                                       \
-        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(p);                          \
+        QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);                                           \
+        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(q_);                         \
     } while (0)
     const int gd = (TASK == QDX_TASK_NONE) ? 0 : (p.grid.dd ? p.grid.dd : -p.cvt.dd);
     if (TASK == QDX_TASK_ARM) {            // arm descriptors are 2-D: grid 2, bucket index 2, or none
@@ -1117,7 +1177,8 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
             unsigned g_ = 0;
             int rc_ = generate_grid(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, smem, p.B, &g_);
             if (rc_) return rc_;
-            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(p);
+            QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);
+            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(q_);
         } else {
             QDX_LAUNCH_GEN(0);
         }
@@ -1316,9 +1377,23 @@ int qdx_score(int32_t task, const float* genotypes, int64_t B, int64_t D, int32_
     if (B == 0) return 0;
     const size_t smem = 4 * 32 * (64 + 1) * sizeof(float);
     const dim3 g((unsigned)((B + 127) / 128));
-    if (task == QDX_TASK_ARM) qdx_score_kernel<QDX_TASK_ARM><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
-    else if (task == QDX_TASK_RASTRIGIN) qdx_score_kernel<QDX_TASK_RASTRIGIN><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
-    else qdx_score_kernel<QDX_TASK_SPHERE><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc);
+    if (task == QDX_TASK_ARM) qdx_score_kernel<QDX_TASK_ARM><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc, QdxNoise{});
+    else if (task == QDX_TASK_RASTRIGIN) qdx_score_kernel<QDX_TASK_RASTRIGIN><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc, QdxNoise{});
+    else qdx_score_kernel<QDX_TASK_SPHERE><<<g, 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, desc_dim, out_fitness, out_desc, QdxNoise{});
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_score_noisy_arm(const float* genotypes, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float fit_variance, float desc_variance,
+                        float params_variance, float* out_fitness, float* out_desc, void* stream) {
+    if (!genotypes || !out_fitness || !out_desc || B < 0 || D <= 0) return QDX_ERR_ARG;
+    if (B == 0) return 0;
+    const QdxKey key{k0, k1};
+    QdxNoise nz;
+    nz.kf = h_split(key, 1); nz.kd = h_split(key, 2); nz.kp = h_split(key, 3);            // arm.py:65: key, f_sub, d_sub, p_sub = split(key, 4)
+    nz.fit_var = fit_variance; nz.desc_var = desc_variance; nz.params_var = params_variance;
+    const size_t smem = 4 * 32 * (64 + 1) * sizeof(float);
+    qdx_score_kernel<QDX_TASK_ARM, true><<<(unsigned)((B + 127) / 128), 128, smem, S(stream)>>>(genotypes, B, (int32_t)D, 2, out_fitness, out_desc, nz);
     QDX_CHECK_LAUNCH();
     return 0;
 }

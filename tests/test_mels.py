@@ -130,3 +130,105 @@ def test_gpu_mels_bit_exact_vs_oracle(dev, co, S, tie_break):
         assert np.array_equal(N(rep.fitnesses).ravel(), cf), f"fitnesses differ at iteration {it}"
         assert np.array_equal(N(rep.genotypes), cg) and np.array_equal(N(rep.descriptors), cd) and np.array_equal(N(rep.spreads), cs)
     assert (~np.isinf(cf)).sum() > 20
+
+
+# ------------------------------------------------------------------------------------------------- noisy arm + MELS end to end
+def test_noisy_arm_oracles_agree(co):
+    """noisy_arm_scoring_function (qdax/tasks/arm.py:53-81): literal NumPy restatement vs the exact-arithmetic C twin."""
+    from oracle import jax_prng as jr
+
+    rng = np.random.default_rng(3)
+    g = rng.random((200, 24)).astype(np.float32)
+    for key, (fv, dv, pv) in [(jr.key(1), (0.01, 0.01, 0.05)), (jr.key(2), (0.0, 0.0, 0.0)), (jr.key(9), (0.3, 0.0, 0.0))]:
+        f1, d1 = co.noisy_arm(g, key, fv, dv, pv)
+        f2, d2 = qn.noisy_arm_scoring_function(g, key, fv, dv, pv)
+        assert np.allclose(f1, f2, rtol=1e-5, atol=1e-6) and np.allclose(d1, d2, rtol=1e-5, atol=1e-6)
+    f0, d0 = co.score("arm", g)
+    f3, d3 = co.noisy_arm(g, jr.key(2), 0.0, 0.0, 0.0)      # x + 0 * n = x: zero variances reduce to the deterministic arm
+    assert np.array_equal(f0, f3) and np.array_equal(d0, d3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,D", [(1, 4), (33, 20), (1000, 100), (130, 200)])
+def test_gpu_noisy_arm_bit_exact(dev, co, B, D):
+    from oracle import jax_prng as jr
+    from qdax_b200.tasks.arm import noisy_arm_scoring_function
+
+    g = np.random.default_rng(B).random((B, D)).astype(np.float32)
+    f, d, extra = noisy_arm_scoring_function(T(g, dev), jr.key(5), fit_variance=0.01, desc_variance=0.02, params_variance=0.05)
+    fo, do = co.noisy_arm(g, jr.key(5), 0.01, 0.02, 0.05)
+    assert extra == {} and np.array_equal(N(f), fo) and np.array_equal(N(d), do)
+    fn, dn = qn.noisy_arm_scoring_function(g, jr.key(5), 0.01, 0.02, 0.05)
+    assert np.allclose(N(f), fn, rtol=1e-5, atol=1e-6) and np.allclose(N(d), dn, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch_size,custom_repertoire", [(1, False), (10, False), (10, True), (64, False)])
+def test_gpu_mels_end_to_end(dev, co, batch_size, custom_repertoire):
+    """reference tests/core_test/mels_test.py:25-183 (MELS, and MAPElites + multi_sample_scoring_function + MELSRepertoire.init;
+    5 samples, 5 iterations; it only asserts `repertoire is not None`) with the noisy arm as the stochastic task -- and every
+    iteration compared with the oracle: emit, num_samples noisy evaluations with split(key, num_samples), MELSRepertoire.add."""
+    import functools
+
+    from oracle import jax_prng as jr
+    from qdax_b200 import lax as qlax
+    from qdax_b200 import random as qr
+    from qdax_b200.core.containers.mapelites_repertoire import compute_euclidean_centroids
+    from qdax_b200.core.containers.mels_repertoire import MELSRepertoire
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+    from qdax_b200.core.map_elites import MAPElites
+    from qdax_b200.core.mels import MELS
+    from qdax_b200.tasks.arm import noisy_arm_scoring_function
+    from qdax_b200.utils.metrics import default_qd_metrics
+    from qdax_b200.utils.sampling import multi_sample_scoring_function
+
+    S, D, iters = 5, 20, 5
+    var = dict(fit_variance=0.01, desc_variance=0.02, params_variance=0.05)
+    scoring = functools.partial(noisy_arm_scoring_function, **var)
+    em = MixingEmitter(lambda x, y: (x, y), functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, batch_size)
+    metrics_fn = functools.partial(default_qd_metrics, qd_offset=0.0)
+    if custom_repertoire:
+        mels = MAPElites(functools.partial(multi_sample_scoring_function, scoring_fn=scoring, num_samples=S), em, metrics_fn,
+                         repertoire_init=MELSRepertoire.init)
+    else:
+        mels = MELS(scoring, em, metrics_fn, num_samples=S)
+    cent = compute_euclidean_centroids((8, 8), 0.0, 1.0, device=dev)
+    cent_h, K = N(cent), 64
+    key = qr.key(42)
+    key, subkey = qr.split(key)
+    init = qr.uniform(subkey, (batch_size, D), device=dev)
+    key, subkey = qr.split(key)
+    rep, state, metrics0 = mels.init(init, cent, subkey)
+    assert isinstance(rep, MELSRepertoire)
+
+    def oracle_scores(x, score_key):
+        ks = jr.split(score_key, S)                                  # sampling.py:137
+        outs = [co.noisy_arm(x, ks[s], var["fit_variance"], var["desc_variance"], var["params_variance"]) for s in range(S)]
+        return np.stack([o[0] for o in outs], axis=1), np.stack([o[1] for o in outs], axis=1)
+
+    # init: key, s = split(subkey); scoring(init, s)  (map_elites.py:81-82)
+    f_all, d_all = oracle_scores(N(init), jr.split(subkey)[1])
+    pop = co.mels_add(np.zeros((K, D), np.float32), np.full(K, -INF, np.float32), np.zeros((K, 2), np.float32), np.full(K, INF, np.float32),
+                      cent_h, N(init), d_all, f_all)
+    assert np.array_equal(N(rep.fitnesses).ravel(), pop[1]) and np.array_equal(N(rep.genotypes), pop[0]) and np.array_equal(N(rep.spreads), pop[3])
+
+    okey = np.array(key, dtype=np.uint32)
+    carry = (rep, state, key)
+    for it in range(iters):
+        carry, m = mels.scan_update(carry, None)
+        ks = jr.split(okey)
+        okey, sub = ks[0], ks[1]
+        ku, a = jr.split(sub)                                        # map_elites.py:177
+        x, _, _ = co.emit_isoline(pop[0], pop[1], jr.split(a)[1], batch_size, 0.05, 0.1, 0.0, 1.0)    # :241
+        f_all, d_all = oracle_scores(x, jr.split(ku)[1])             # :181
+        pop = co.mels_add(pop[0], pop[1], pop[2], pop[3], cent_h, x, d_all, f_all)
+        r = carry[0]
+        assert np.array_equal(N(r.fitnesses).ravel(), pop[1]), it
+        assert np.array_equal(N(r.genotypes), pop[0]) and np.array_equal(N(r.descriptors), pop[2]) and np.array_equal(N(r.spreads), pop[3]), it
+        ref = co.metrics(pop[1], 0.0)
+        assert np.isclose(float(m["qd_score"]), ref[0], rtol=1e-5, atol=1e-6) and np.isclose(float(m["coverage"]), ref[2], rtol=1e-6)
+    assert (np.array(carry[2]) == okey).all()
+    # the jax.lax.scan idiom of the reference test
+    (rep_s, _, key_s), ms = qlax.scan(mels.scan_update, (rep, state, key), (), length=iters)
+    assert torch.equal(rep_s.genotypes, carry[0].genotypes) and torch.equal(rep_s.spreads, carry[0].spreads) and (np.array(key_s) == okey).all()
