@@ -255,6 +255,11 @@ int qdx_map_elites_step(const qdx_step_desc* step, int32_t key_mode, uint32_t k0
 /* ---- pieces of the preserved Python surface ---- */
 /* UniformSelector.select index stream for the key handed to select() (uniform_selector.py:48-55) */
 int qdx_select_indices(void* ws, uint32_t k0, uint32_t k1, int64_t num, int32_t* out, void* stream);
+/* UniformSelector(select_with_replacement=False).select index stream (uniform_selector.py:19-20, :49-55: jax.random.choice with
+ * replace=False = Gumbel top-k); the workspace's selection tables must describe rep_fitness (qdx_select_prepare / qdx_commit);
+ * scratch_K: K floats; num <= K <= 2^18. */
+int qdx_select_indices_without_replacement(const float* rep_fitness, int64_t K, void* ws, uint32_t k0, uint32_t k1, int64_t num, float* scratch_K,
+                                           int32_t* out, void* stream);
 int qdx_gather_rows(const float* src, const int32_t* idx, int64_t B, int64_t D, float* out, void* stream);
 /* isoline_variation(x1, x2, key, ...) on dense parents (mutation_operators.py:175-226) */
 int qdx_isoline_variation(const float* x1, const float* x2, int64_t B, int64_t D, uint32_t k0, uint32_t k1, float iso_sigma,

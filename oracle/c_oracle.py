@@ -131,6 +131,13 @@ def select_indices(fitnesses, key, num: int) -> np.ndarray:
     return out
 
 
+def select_indices_without_replacement(fitnesses, key, num: int) -> np.ndarray:
+    f = _f(fitnesses).reshape(-1)
+    out = np.zeros(num, dtype=np.int32)
+    _chk(lib().qo_select_indices_noreplace(_p(f), C.c_int64(f.size), _p(_key(key)), C.c_int64(num), _p(out)), "select_noreplace")
+    return out
+
+
 def _clip_args(minval, maxval):
     return (
         C.c_int(minval is not None), C.c_float(0.0 if minval is None else minval),

@@ -280,6 +280,26 @@ def uniform_select_indices(fitnesses: np.ndarray, key: np.ndarray, num_samples: 
     return jr.choice_p_replace(sub, p, num_samples)  # :49-55
 
 
+def uniform_select_indices_without_replacement(fitnesses: np.ndarray, key: np.ndarray, num_samples: int) -> np.ndarray:
+    """UniformSelector(select_with_replacement=False) (uniform_selector.py:19-20, :49-55): jax.random.choice(subkey, arange(K),
+    (n,), p=p, replace=False) is the Gumbel top-k trick [recalled from jax/_src/random.py]: g = gumbel(key, (K,)) + log(p),
+    gumbel = -log(-log(uniform(key, (K,), minval=tiny, maxval=1))); indices = top_k(g, n) (equal values: lower index first).
+    Empty cells have log(0) = -inf and come last.  PARITY UNPINNED (XLA's log, and jax's gumbel sampling mode)."""
+    f = np.asarray(fitnesses)
+    empty = np.any(f.reshape(len(f), -1) == NEG_INF, axis=-1)  # :44
+    occ = (F32(1.0) - empty.astype(F32)).astype(F32)
+    p = (occ / F32(np.sum(occ, dtype=np.float64))).astype(F32)  # :45
+    sub = jr.split(key)[1]  # :48
+    K = p.shape[0]
+    if num_samples > K:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    u = jr.uniform(sub, (K,), np.finfo(F32).tiny, 1.0)
+    with np.errstate(divide="ignore"):
+        g = (-np.log((-np.log(u)).astype(F32))).astype(F32)
+        g = (g + np.log(p).astype(F32)).astype(F32)
+    return np.argsort(-g, kind="stable")[:num_samples].astype(np.int32)
+
+
 # --------------------------------------------------------------------------------------
 # variation -- emitters/mutation_operators.py
 # --------------------------------------------------------------------------------------

@@ -284,6 +284,42 @@ QO_API int qo_select_indices(const float* fit, int64_t K, const uint32_t* key, i
     return select_indices(fit, K, k, num, out);
 }
 
+/* UniformSelector(select_with_replacement=False) -- jax.random.choice(..., p=p, replace=False): Gumbel top-k.
+ * g_c = -log(-log(u_c)) + log(p_c), u = uniform(subkey, (K,), minval=tiny, maxval=1); indices = top_k(g, n), equal values:
+ * lower index first; empty cells (p = 0, log = -inf) come last. */
+typedef struct { float g; int32_t c; } qo_gc;
+static int gc_cmp(const void* a, const void* b) {
+    const qo_gc* x = (const qo_gc*)a; const qo_gc* y = (const qo_gc*)b;
+    if (x->g > y->g) return -1;
+    if (x->g < y->g) return 1;
+    return (x->c > y->c) - (x->c < y->c);
+}
+QO_API int qo_select_indices_noreplace(const float* fit, int64_t K, const uint32_t* key, int64_t num, int32_t* out) {
+    if (num > K) return -1;
+    int64_t M = 0;
+    for (int64_t c = 0; c < K; ++c) M += (fit[c] != -INFINITY);
+    if (M == 0) return -3;
+    qo_gc* v = (qo_gc*)malloc(sizeof(qo_gc) * (size_t)K);
+    if (!v) return -2;
+    qo_key k = {key[0], key[1]};
+    qo_key sub = split_i(k, 1);
+    const float q = 1.0f / (float)M;
+    const float logq = spec_logf(q);
+    const float tiny = 0x1p-126f;
+    for (int64_t c = 0; c < K; ++c) {
+        float f = unit_float(bits32(sub, (uint64_t)c));
+        float u = f * 1.0f + tiny;                      /* f * (maxval - minval) + minval, maxval - minval = fl(1 - tiny) = 1 */
+        if (u < tiny) u = tiny;
+        float g = -spec_logf(-spec_logf(u));
+        v[c].g = (fit[c] != -INFINITY) ? g + logq : -INFINITY;
+        v[c].c = (int32_t)c;
+    }
+    qsort(v, (size_t)K, sizeof(qo_gc), gc_cmp);
+    for (int64_t i = 0; i < num; ++i) out[i] = v[i].c;
+    free(v);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ isoline variation
  * qdax/core/emitters/mutation_operators.py:175-226 (single-leaf genotype).
  * x = (x1 + iso) + (x2 - x1) * line ; clip.  Parents given by index into a (K, D) table when

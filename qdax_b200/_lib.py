@@ -125,6 +125,7 @@ PROTOTYPES = {
     "qdx_offer_cells": [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _i32, _vp],
     "qdx_commit": [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _u32, _i64, _i32, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
     "qdx_select_indices": [_vp, _u32, _u32, _i64, _vp, _vp],
+    "qdx_select_indices_without_replacement": [_vp, _i64, _vp, _u32, _u32, _i64, _vp, _vp, _vp],
     "qdx_gather_rows": [_vp, _vp, _i64, _i64, _vp, _vp],
     "qdx_isoline_variation": [_vp, _vp, _i64, _i64, _u32, _u32, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp],
     "qdx_generate_leaves": [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, C.POINTER(_u32),
@@ -171,7 +172,7 @@ def lib() -> C.CDLL:
 
 # every C-ABI call that launches at least one of OUR kernels: name -> launches per call (bench.py `gpu_launches`)
 KERNEL_LAUNCHES = {"qdx_select_prepare": 1, "qdx_regenerate_winners": 1, "qdx_elect_winners": 1, "qdx_xchg_push": 1, "qdx_generate": 1, "qdx_generate_leaves": 1, "qdx_isoline_variation_leaves": 1, "qdx_copy_2d": 1, "qdx_kmeans_accumulate": 1, "qdx_kmeans_update": 1, "qdx_mels_offer": 1, "qdx_mome_add": 1, "qdx_unstructured_plan": 3, "qdx_unstructured_offer": 3, "qdx_scatter_rows_by_source": 1, "qdx_score": 1, "qdx_score_noisy_arm": 1, "qdx_cells": 1, "qdx_cells_indexed": 1, "qdx_cells_tc": 2, "qdx_cells_tc_prepare": 1, "qdx_offer_cells": 1,
-                   "qdx_commit": 1, "qdx_select_indices": 1, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
+                   "qdx_commit": 1, "qdx_select_indices": 1, "qdx_select_indices_without_replacement": 2, "qdx_gather_rows": 1, "qdx_isoline_variation": 1, "qdx_polynomial_mutation": 1, "qdx_polynomial_crossover": 1,
                    "qdx_random": 1, "qdx_metrics": 1, "qdx_dns_add": 3}
 launch_count = 0
 

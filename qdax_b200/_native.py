@@ -557,6 +557,18 @@ def select_indices(ws: Workspace, key, num: int, device) -> torch.Tensor:
     return out
 
 
+def select_indices_without_replacement(rep_f: torch.Tensor, ws: Workspace, key, num: int) -> torch.Tensor:
+    k0, k1 = key_words(key)
+    K = rep_f.numel()
+    if num > K:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    out = torch.empty(num, dtype=torch.int32, device=rep_f.device)
+    scratch = torch.empty(K, dtype=torch.float32, device=rep_f.device)
+    call("qdx_select_indices_without_replacement", _ptr(rep_f), C.c_int64(K), ws.ptr, C.c_uint32(k0), C.c_uint32(k1), C.c_int64(num), _ptr(scratch),
+         _ptr(out), _stream())
+    return out
+
+
 def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     src2 = src.reshape(src.shape[0], -1)
     out = torch.empty((idx.numel(), src2.shape[1]), dtype=torch.float32, device=src.device)

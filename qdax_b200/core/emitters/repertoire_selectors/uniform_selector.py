@@ -1,7 +1,8 @@
 """UniformSelector -- mirrors qdax/core/emitters/repertoire_selectors/uniform_selector.py:14-62.
 
 select(): p = occupied / sum(occupied); key, subkey = split(key); choice(subkey, arange(K), (n,), p=p); gather
-every field.  On the GPU: an occupancy scan builds the occupied-cell list and the float32 running-sum segments
+every field (select_with_replacement=False: the Gumbel top-k trick of jax.random.choice, qdx_select_indices_without_replacement).
+On the GPU: an occupancy scan builds the occupied-cell list and the float32 running-sum segments
 (qdx_select_prepare), qdx_select_indices draws the index stream, qdx_gather_rows gathers the rows."""
 
 from __future__ import annotations
@@ -18,8 +19,6 @@ class UniformSelector(Selector):
 
     def select_indices(self, repertoire, key, num_samples: int) -> torch.Tensor:
         """The index stream of `select` (int32, device)."""
-        if not self.select_with_replacement:
-            raise NotImplementedError("select_with_replacement=False (Gumbel top-k in jax.random.choice) is not on the accelerated path")
         rep = unfold_repertoire(repertoire)
         f = _native.require_cuda(rep.fitnesses, "fitnesses")
         if f.dim() == 2 and f.shape[1] != 1:
@@ -27,6 +26,8 @@ class UniformSelector(Selector):
         ws = rep._workspace()
         ws.raise_if_error()
         _native.ensure_selection(f.reshape(-1), ws)
+        if not self.select_with_replacement:     # jax.random.choice(replace=False): Gumbel top-k (reference :19-20, :54)
+            return _native.select_indices_without_replacement(f.reshape(-1), ws, key, num_samples)
         return _native.select_indices(ws, key, num_samples, f.device)
 
     def select(self, repertoire, key, num_samples: int):

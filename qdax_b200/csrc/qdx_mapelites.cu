@@ -973,6 +973,41 @@ __global__ void __launch_bounds__(256) qdx_select_kernel(void* ws_raw, QdxKey ke
     out[i] = qdx_ws_occ(ws_raw)[qdx_sel_rank(s_seg, s_last, nseg, ws->sel.total * (1.0f - u)) - 1];
 }
 
+// UniformSelector(select_with_replacement=False): jax.random.choice(subkey, arange(K), (n,), p=p, replace=False) is the Gumbel
+// top-k trick: g_c = -log(-log(u_c)) + log(p_c), u = uniform(subkey, (K,), minval=tiny, maxval=1); the n largest g, equal
+// values by ascending cell.  Empty cells have p = 0, log = -inf: they come last (and are returned when n exceeds the number
+// of occupied cells, as in the reference).
+__global__ void __launch_bounds__(256) qdx_gumbel_kernel(const float* __restrict__ rep_f, int64_t K, const void* ws_raw, QdxKey key,
+                                                         float* __restrict__ g) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    const QdxWorkspace* ws = (const QdxWorkspace*)ws_raw;
+    const int32_t M = ws->sel.M;
+    if (M <= 0) { if (c == 0) qdx_set_error((void*)ws_raw, QDX_ERR_EMPTY_REPERTOIRE); g[c] = -INFINITY; return; }
+    const QdxKey sub = qdx_split(key, 1);                                           // uniform_selector.py:48
+    const float tiny = 0x1p-126f;
+    float u = qdx_unit_float(qdx_bits32(sub, (uint64_t)c)) * 1.0f + tiny;            // f * (maxval - minval) + minval
+    u = u < tiny ? tiny : u;
+    const float gum = -qdx_logf(-qdx_logf(u));
+    const float logq = qdx_logf(__fdiv_rn(1.0f, (float)M));
+    g[c] = (__ldg(rep_f + c) != -INFINITY) ? gum + logq : -INFINITY;
+}
+// rank of every cell in the descending order of g (ties: ascending cell) by counting, candidate tiles through shared memory
+__global__ void __launch_bounds__(256) qdx_topk_rank_kernel(const float* __restrict__ g, int64_t K, int64_t n, int32_t* __restrict__ out) {
+    __shared__ float s_g[1024];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float mine = c < K ? g[c] : 0.0f;
+    int64_t rank = 0;
+    for (int64_t j0 = 0; j0 < K; j0 += 1024) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_g[i] = j0 + i < K ? g[j0 + i] : -INFINITY;
+        __syncthreads();
+        const int m = (K - j0) < 1024 ? (int)(K - j0) : 1024;
+        for (int i = 0; i < m; ++i) { const float v = s_g[i]; rank += (v > mine) || (v == mine && j0 + i < c); }
+    }
+    if (c < K && rank < n) out[rank] = (int32_t)c;
+}
+
 // out[i, :] = src[idx[i], :]
 __global__ void __launch_bounds__(256) qdx_gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                                               int64_t B, int32_t D, float* __restrict__ out) {
@@ -1144,15 +1179,15 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) 
     return 0;
 }
 
-// Tile height: the rows of one warp (B / warps of the grid) cut into the fewest tiles of at most 32 rows, all the same size.
-static int32_t generate_tile_rows(int64_t B, unsigned ctas) {
-    const int64_t warps = (int64_t)ctas * QDX_GEN_WARPS;
-    const int64_t per_warp = (B + warps - 1) / warps;                   // ceil
-    if (per_warp <= 32) return 32;                                       // at most one tile per warp: full tiles
-    const int64_t tiles = (per_warp + 31) / 32;
-    const int64_t rows = (per_warp + tiles - 1) / tiles;
-    return (int32_t)(rows < 8 ? 8 : rows);
-}
+// Tile height.  Measured on B200 (tools/time_generate.py, arm 100-D, rows per launch 131 072 / 262 144 / 2^20; in-kernel span):
+//   one 32-row tile per warp, ceil(B / 128) CTAs (hardware CTA scheduler)        93.4 / 177.3 / 677 us
+//   persistent, static equal split of the rows                                   99.3 / 194.1 / 737 us   (warps progress unevenly)
+//   persistent, dynamic, guided (tiles shrinking from 32 to 8 rows)             100.9 / 179.4 / 676 us   (row-serial scoring phase costs the same for 8 rows as for 32)
+//   persistent, dynamic, equal tiles of 28 rows (whole tiles per warp)           96.0 / 203.1 / 674 us
+//   persistent, dynamic, 32-row tiles                                            this build
+// The tail of the kernel is the lowest-priority warp of every SM sub-partition finishing its last tile alone, at
+// single-warp issue rate; smaller last tiles shorten it but pay the fixed per-tile cost of the lane = row scoring phase.
+static int32_t generate_tile_rows(int64_t, unsigned) { return 32; }
 
 template <int TASK, bool ARM_CLIP>
 static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t st) {
@@ -1614,6 +1649,19 @@ int qdx_select_indices(void* ws, uint32_t k0, uint32_t k1, int64_t num, int32_t*
     if (!ws || !out || num < 0) return QDX_ERR_ARG;
     if (num == 0) return 0;
     qdx_select_kernel<<<(unsigned)((num + 255) / 256), 256, 0, S(stream)>>>(ws, QdxKey{k0, k1}, num, out);
+    QDX_CHECK_LAUNCH();
+    return 0;
+}
+
+int qdx_select_indices_without_replacement(const float* rep_fitness, int64_t K, void* ws, uint32_t k0, uint32_t k1, int64_t num, float* scratch_K,
+                                           int32_t* out, void* stream) {
+    if (!rep_fitness || !ws || !scratch_K || !out || K <= 0 || num < 0) return QDX_ERR_ARG;
+    if (num > K) return QDX_ERR_ARG;                 // "Cannot take a larger sample than population when 'replace=False'"
+    if (K > (1ll << 18)) return QDX_ERR_UNSUPPORTED;  // rank by counting: K^2 comparisons
+    if (num == 0) return 0;
+    const unsigned g = (unsigned)((K + 255) / 256);
+    qdx_gumbel_kernel<<<g, 256, 0, S(stream)>>>(rep_fitness, K, ws, QdxKey{k0, k1}, scratch_K);
+    qdx_topk_rank_kernel<<<g, 256, 0, S(stream)>>>(scratch_K, K, num, out);
     QDX_CHECK_LAUNCH();
     return 0;
 }
