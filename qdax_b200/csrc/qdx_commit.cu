@@ -477,6 +477,7 @@ __device__ __forceinline__ T* shfl_ptr(T* p, int src) {
 }
 
 __global__ void __launch_bounds__(LEAN_THREADS) qdx_commit_lean_kernel(const CommitParams p, int32_t) {
+    qdx_pdl_enter();         // keys, offspring rows and fitnesses read below are the previous kernel's (generate / cells) output
     QdxWorkspace* ws = (QdxWorkspace*)p.ws;
     unsigned long long* keytab = qdx_ws_keytab(p.ws, p.K);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -686,8 +687,7 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
     if (mode == 3 || (mode != 1 && D <= 256)) {
         int64_t ctas = (K + LEAN_THREADS - 1) / LEAN_THREADS;
         if (ctas > QDX_MAX_COMMIT_CTAS) ctas = QDX_MAX_COMMIT_CTAS;
-        qdx_commit_lean_kernel<<<(unsigned)ctas, LEAN_THREADS, 0, (cudaStream_t)stream>>>(p, 0);
-        return (int)cudaGetLastError();
+        return (int)qdx_launch_pdl(qdx_commit_lean_kernel, dim3((unsigned)ctas), dim3(LEAN_THREADS), 0, (cudaStream_t)stream, p, 0);
     }
     DeviceCaps caps;
     int rc = device_caps(&caps);

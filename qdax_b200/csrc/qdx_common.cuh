@@ -1,6 +1,7 @@
 // Shared device-side structures of the MAP-Elites generation step (B200 / sm_100a).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "qdx_math.cuh"
 #include "qdx_select.cuh"
@@ -285,6 +286,31 @@ static __device__ __noinline__ void qdx_cta_occupancy_scan(const float* rep_f, i
 }
 
 
+// ---- programmatic dependent launch (generate -> lean commit -> generate ...): the next kernel of the generation chain is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled while the previous kernel
+// drains and only its first instruction waits for the previous grid to complete and flush (griddepcontrol.wait) -- the
+// ~3-4 us launch gap between two dependent kernels disappears from a ~100 us generation.  QDX_PDL=0 in the environment
+// turns the attribute off (A/B); kernels launched without it see both instructions as no-ops.
+QDX_DEV void qdx_pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+static inline bool qdx_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("QDX_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t qdx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = qdx_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 #ifndef QDX_XCHG_TRACE
 #define QDX_XCHG_TRACE 0      // timing experiments only: where a multi-GPU generation's tail goes (qdx_debug_xchg_trace)
 #endif
@@ -304,20 +330,28 @@ QDX_DEV unsigned long long qdx_ld_acquire_sys(const unsigned long long* p) {
     return v;
 }
 
-// Publication of "rank `me`, epoch e: all my keys have landed": this rank's generation keys go to slot `me` of every
-// rank's table (the winners are REGENERATED by every rank from (owner's keys, local index), so no genotype crosses
-// NVLink), then the arrival flag is raised in every peer (release, system scope).  One thread.
+QDX_DEV void qdx_st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Publication of "rank `me`, epoch e: all my keys (and offspring rows) have landed": the arrival flag is raised in every
+// peer.  One thread, after it has observed that every CTA of the offering kernel is done (ticket + fence): everything those
+// CTAs wrote -- key pushes into the peers, rows / fitnesses / descriptors in this rank's offspring block -- is ordered
+// before the flags by ONE system-scope fence (cumulativity), followed by relaxed system-scope stores; a consumer that
+// acquires the flag sees all of it.  Keys-only exchange (no offspring blocks: the winners are REGENERATED by every rank
+// from (owner's keys, local index)): this rank's generation keys go to slot `me` of every rank's table first.
 QDX_DEV void qdx_xchg_publish(QdxWorkspace* ws, int64_t K, const QdxGenKeys& keys) {
     const int R = ws->xchg_nranks, me = ws->xchg_rank;
     const uint32_t epoch = *(const uint32_t*)((const char*)ws->xchg_peer[me] + QDX_XCHG_EPOCH_OFFSET);
-    const size_t off = qdx_xchg_tab_offset(K, (int)(epoch & 1u));
-    const uint32_t w[8] = {keys.sel1.a, keys.sel1.b, keys.sel2.a, keys.sel2.b, keys.line.a, keys.line.b, keys.leaf.a, keys.leaf.b};
-    __threadfence_system();
-    for (int q = 0; q < R; ++q) {
-        unsigned long long* slot = (unsigned long long*)((char*)ws->xchg_peer[q] + off) + K + 8 * me;
+    if (ws->xchg_bdev == 0) {
+        const size_t off = qdx_xchg_tab_offset(K, (int)(epoch & 1u));
+        const uint32_t w[8] = {keys.sel1.a, keys.sel1.b, keys.sel2.a, keys.sel2.b, keys.line.a, keys.line.b, keys.leaf.a, keys.leaf.b};
+        for (int q = 0; q < R; ++q) {
+            unsigned long long* slot = (unsigned long long*)((char*)ws->xchg_peer[q] + off) + K + 8 * me;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) slot[j] = (unsigned long long)w[j];
+            for (int j = 0; j < 8; ++j) slot[j] = (unsigned long long)w[j];
+        }
     }
     __threadfence_system();
-    for (int q = 0; q < R; ++q) qdx_st_release_sys((unsigned long long*)ws->xchg_peer[q] + me, (unsigned long long)(epoch + 1u));
+    for (int q = 0; q < R; ++q) qdx_st_relaxed_sys((unsigned long long*)ws->xchg_peer[q] + me, (unsigned long long)(epoch + 1u));
 }

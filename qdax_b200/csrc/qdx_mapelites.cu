@@ -151,7 +151,7 @@ QDX_DEV void qdx_bulk_store(void* gptr, const void* sptr, uint32_t bytes) {
 // generation); `sys`: the row will be read by peer GPUs, fence at system scope.
 QDX_DEV void qdx_store_row(float* __restrict__ dst, const float* src_smem, int n, int sys) {
     for (int d = 0; d < n; d += 4) *reinterpret_cast<float4*>(dst + d) = *reinterpret_cast<const float4*>(src_smem + d);
-    if (sys) __threadfence_system();
+    (void)sys;      // ordered before the arrival flags by the publisher's fence (see qdx_xchg_publish)
 }
 
 constexpr int QDX_GEN_WARPS = 4;
@@ -177,6 +177,7 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p);
 // MULTI: the packed row is the concatenation of several pytree leaves, each with its own noise key and counter space.
 template <int TASK, int GRID_DD, bool ARM_CLIP, bool MULTI = false>
 __global__ void __launch_bounds__(QDX_GEN_WARPS * 32, 4) qdx_generate_kernel(const QdxGenParams p) {
+    qdx_pdl_enter();         // the selection tables / repertoire rows read below are the previous kernel's (commit) output
     QDX_GEN_STAMP(0, atomicMin); QDX_GEN_STAMP(1, atomicMax);
     qdx_generate_body<TASK, GRID_DD, ARM_CLIP, MULTI>(p);
 #if QDX_GEN_TRACE
@@ -270,7 +271,10 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         const uint32_t qmagic = (1u << 20) / (uint32_t)q + 1u;   // qi / q == (qi * qmagic) >> 20 for qi * q < 2^20
         // ---- phase 1: gene-parallel variation over the tile ---------------------------------------------
         // All 32 lanes stay converged (lanes past the end recompute the last quad and skip the store), so the
-        // normal transform can vote with a full mask.  (2x unrolling measured: no gain, profiles/r1_notes.md.)
+        // normal transform can vote with a full mask.  (Measured, no gain: 2x unrolling (profiles/r1_notes.md); a software
+        // pipeline that issues the NEXT quad's Threefry blocks next to the current quad's float transforms, to mix ALU- and
+        // FMA-pipe work inside one warp: 0.710 vs 0.680 ms -- ptxas keeps the two streams apart, co-resident warps already
+        // mix them (profiles/r2_notes.md).)
         const int total_quads = nrows * q;
         for (int qb = 0; qb < total_quads; qb += 32) {
             const bool act = qb + lane < total_quads;
@@ -435,10 +439,12 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         __syncwarp();
     }
     }   // tiles of this warp
-    if (p.out_xchg) {
-        // peers read these rows straight out of this rank's memory once its arrival flag is up (qdx_xchg_cta_done): the
-        // bulk copies must have COMPLETED (not merely been read out of shared memory) and be visible at system scope
-        if (out_g && p.store_mode == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    if (p.out_xchg && out_g && p.store_mode == 0) {
+        // peers read these rows straight out of this rank's memory once its arrival flag is up: the bulk copies must have
+        // COMPLETED (not merely been read out of shared memory).  Ordinary stores (fitness / descriptors of every row, fired
+        // rows) need nothing here: they are ordered before the flags by the CTA barrier, the ticket and the publisher's
+        // system-scope fence (a fence per warp at this point cost ~20 us per launch: MEMBAR.SYS serialises within an SM).
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
         __threadfence_system();
     }
 }
@@ -1197,7 +1203,8 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
         int rc_ = generate_grid(qdx_generate_kernel<TASK, GD, ARM_CLIP>, smem, p.B, &g_);                          \
         if (rc_) return rc_;                                                                                       \
         QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);                                           \
-        qdx_generate_kernel<TASK, GD, ARM_CLIP><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(q_);                         \
+        cudaError_t e_ = qdx_launch_pdl(qdx_generate_kernel<TASK, GD, ARM_CLIP>, dim3(g_), dim3(QDX_GEN_WARPS * 32), smem, st, q_); \
+        if (e_ != cudaSuccess) return (int)e_;                                                                     \
     } while (0)
     const int gd = (TASK == QDX_TASK_NONE) ? 0 : (p.grid.dd ? p.grid.dd : -p.cvt.dd);
     if (TASK == QDX_TASK_ARM) {            // arm descriptors are 2-D: grid 2, bucket index 2, or none
@@ -1213,7 +1220,8 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
             int rc_ = generate_grid(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, smem, p.B, &g_);
             if (rc_) return rc_;
             QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);
-            qdx_generate_kernel<QDX_TASK_NONE, 0, false, true><<<g_, QDX_GEN_WARPS * 32, smem, st>>>(q_);
+            cudaError_t e_ = qdx_launch_pdl(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, dim3(g_), dim3(QDX_GEN_WARPS * 32), smem, st, q_);
+            if (e_ != cudaSuccess) return (int)e_;
         } else {
             QDX_LAUNCH_GEN(0);
         }

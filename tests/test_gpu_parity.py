@@ -77,6 +77,45 @@ def test_select_from_empty_repertoire_raises(dev):
         rep._workspace().check()
 
 
+def test_device_errors_surface_at_the_next_api_call(dev):
+    """A device-side error never stays silent: the kernels mirror the sticky flag into pinned host memory and
+    every API boundary polls it -- the call after the failing one raises, without any explicit check()."""
+    from qdax_b200._lib import QdxError
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+
+    K = 16
+    rep = MapElitesRepertoire(torch.zeros(K, 4, device=dev), torch.full((K, 1), -np.inf, device=dev), torch.zeros(K, 2, device=dev),
+                              torch.rand(K, 2, device=dev))
+    rep.select(jr.key(0), 4)                       # selection from an all-empty repertoire: flagged on the device
+    torch.cuda.synchronize()
+    with pytest.raises(QdxError, match="EMPTY_REPERTOIRE"):
+        rep.select(jr.key(1), 4)
+    with pytest.raises(QdxError):
+        rep.add(torch.rand(3, 4, device=dev), torch.rand(3, 2, device=dev), torch.rand(3, device=dev))
+
+
+@pytest.mark.parametrize("K,occ,n", [(16, 1.0, 16), (400, 0.3, 100), (400, 0.3, 300), (10000, 0.68, 4096)])
+def test_uniform_selector_without_replacement(dev, co, K, occ, n):
+    """UniformSelector(select_with_replacement=False): the Gumbel top-k index stream, bit-exact vs the C oracle; no index
+    repeats; occupied cells come first (n > occupied returns empty cells last, as jax.random.choice does)."""
+    from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
+    from qdax_b200.core.emitters.repertoire_selectors.uniform_selector import UniformSelector
+
+    rng = np.random.default_rng(K + n)
+    fit = np.where(rng.random(K) < occ, rng.standard_normal(K), -np.inf).astype(np.float32)
+    fit[0] = 0.5
+    g = rng.random((K, 8)).astype(np.float32)
+    rep = MapElitesRepertoire(T(g, dev), T(fit.reshape(-1, 1), dev), torch.zeros(K, 2, device=dev), torch.rand(K, 2, device=dev))
+    sel = UniformSelector(select_with_replacement=False)
+    idx = N(sel.select_indices(rep, jr.key(7), n))
+    ref = co.select_indices_without_replacement(fit, jr.key(7), n)
+    assert np.array_equal(idx, ref) and len(set(idx.tolist())) == n
+    picked = sel.select(rep, jr.key(7), n)
+    assert np.array_equal(N(picked.genotypes), g[ref]) and np.array_equal(N(picked.fitnesses).ravel(), fit[ref])
+    with pytest.raises(ValueError):
+        sel.select_indices(rep, jr.key(7), K + 1)
+
+
 # ------------------------------------------------------------------------------------------------- variation
 @pytest.mark.parametrize("B,D", [(1, 4), (33, 20), (1000, 100), (257, 7)])
 def test_isoline_variation_dense(dev, co, B, D):
