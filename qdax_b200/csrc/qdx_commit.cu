@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
     __shared__ int32_t s_base;
     __shared__ double s_sum[CW]; __shared__ float s_max[CW]; __shared__ int s_cnt[CW], s_nan[CW], s_add[CW], s_occn[CW];
 
+    qdx_pdl_enter();         // keys, offspring rows and fitnesses read below are the previous kernel's output
     QdxWorkspace* ws = (QdxWorkspace*)p.ws;
     unsigned long long* keytab = qdx_ws_keytab(p.ws, p.K);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -704,8 +705,22 @@ extern "C" int qdx_commit(void* ws, int64_t K, int64_t D, int32_t desc_dim, cons
     if (nblk > cap) nblk = cap;
     if (nblk > QDX_MAX_COMMIT_CTAS - 1) nblk = QDX_MAX_COMMIT_CTAS - 1;
     if (nblk < 1) nblk = 1;
-    void* args[] = {(void*)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)qdx_commit_stream_kernel, dim3((unsigned)(nblk + 1)), dim3(CW * 32), args,
-                                                (size_t)CW * NST * CHUNK, (cudaStream_t)stream);
+    // cooperative launch (the grid barrier needs co-residency) + programmatic dependent launch (its CTAs are scheduled while the
+    // previous kernel drains; the first instruction waits for it).  If the runtime refuses the combination, cooperative only.
+    static int pdl_ok = -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nblk + 1)); cfg.blockDim = dim3(CW * 32); cfg.dynamicSmemBytes = (size_t)CW * NST * CHUNK; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_ok != 0 && qdx_pdl_enabled()) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qdx_commit_stream_kernel, p);
+    if (e != cudaSuccess && cfg.numAttrs == 2) {
+        (void)cudaGetLastError();
+        pdl_ok = 0;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, qdx_commit_stream_kernel, p);
+    } else if (e == cudaSuccess && cfg.numAttrs == 2) pdl_ok = 1;
     return e == cudaSuccess ? 0 : (int)e;
 }
