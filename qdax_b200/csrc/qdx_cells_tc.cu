@@ -4,17 +4,20 @@
 // /root/reference): argmin_k sum_d (x_d - c_kd)^2 in float32, sequential over d, FIRST minimum.  The reference
 // never expands the square; neither does the final decision here:
 //
-//   1. tensor pass   d~(i,k) = ||c_k||^2 - 2 x_i . c_k   with x . c from tcgen05.mma kind::tf32 (M=128, N=128, K=32:
-//                    four K=8 steps), FP32 accumulators in TMEM, double buffered; centroid tiles stream through a
-//                    4-stage shared-memory ring filled by 1-D bulk async copies (cp.async.bulk + mbarrier
-//                    complete_tx) from a copy of the centroids that was written ONCE in the 128-byte-swizzled
-//                    K-major layout the UMMA descriptors expect (a 32-float row is exactly one swizzle row, so no
-//                    tensor map is needed); warp roles: 1 copy-issuer, 1 MMA-issuer, 4 epilogue warps (one TMEM
-//                    lane quadrant each, thread = descriptor row).
+//   1. tensor pass   s~(i,k) = x_i . c_k - ||c_k||^2 / 2   (argmin of the distance = argmax of s) entirely on the tensor cores:
+//                    tcgen05.mma kind::tf32 (M=128, N=128), four K=8 steps over the 32 descriptor dimensions plus a FIFTH
+//                    K=8 step that multiplies [1, 1, 1, 0...] by [-||c||^2/2 split into three TF32-exact terms, 0...], so the
+//                    epilogue is a bare running maximum over the accumulator (no ||c||^2 fetch, no FMA per pair);
+//                    FP32 accumulators in TMEM, double buffered; centroid tiles stream through a 4-stage shared-memory
+//                    ring filled by ONE 1-D bulk async copy per tile (cp.async.bulk + mbarrier complete_tx) from a copy
+//                    of the centroids that was written ONCE in the layouts the UMMA descriptors expect: a 16 KB
+//                    128-byte-swizzled K-major block (a 32-float row is exactly one swizzle row, so no tensor map is
+//                    needed) followed by the 4 KB 32-byte-swizzled block of the extra K step; warp roles: 1 copy-issuer,
+//                    1 MMA-issuer, 4 epilogue warps (one TMEM lane quadrant each, thread = descriptor row).
 //                    Both x and c are centred on the centroid mean mu first (distances are translation invariant):
 //                    the TF32 error scales with ||x - mu|| * ||c - mu||, 4x smaller than the uncentred product for
 //                    data in [0,1]^32, and it makes the bound usable for tessellations far from the origin.
-//   2. candidates    every k with d~ <= min_k d~ + band_i is kept (sorted list of T), where band_i bounds twice the
+//   2. candidates    every k with s~ >= max_k s~ - band_i is kept (sorted list of T), where band_i bounds twice the
 //                    TF32 error (|x~c~ - xc| <= 2^-9 |xc| per product, Cauchy-Schwarz over the row) plus twice the
 //                    rounding error of the reference's own float32 sum -- so the list provably contains every index
 //                    that can attain the reference's computed minimum.
@@ -37,10 +40,15 @@ constexpr int STAGES = 4;              // shared-memory ring of centroid tiles
 constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (2 x 128 columns)
 constexpr int TMEM_COLS = ACC_STAGES * TILE_N;
 constexpr int TLIST = 16;              // candidates kept per row
+constexpr int KX = 8;                  // the extra K step (one UMMA_K of tf32 = 32 bytes per row, SWIZZLE_32B)
 constexpr int A_BYTES = TILE_M * KD * 4;        // 16 KB
+constexpr int AX_BYTES = TILE_M * KX * 4;       // 4 KB
 constexpr int B_BYTES = TILE_N * KD * 4;        // 16 KB
+constexpr int BX_BYTES = TILE_N * KX * 4;       // 4 KB
+constexpr int STAGE_BYTES = B_BYTES + BX_BYTES; // one centroid tile: both blocks, contiguous in global memory too
 constexpr int NUM_THREADS = 192;       // warp 0: copies, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + AX_BYTES + STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr float PAD_S = -1.0e30f;      // s of a padding centroid: never the maximum
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,21 +137,27 @@ __device__ __forceinline__ void tmem_wait_ld(float (&v)[32]) {
         :: "memory");
 }
 
-// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptors, K-major.  SWIZZLE_128B: rows of 128 bytes, 8-row atoms 1024 bytes apart (layout type 2);
+// SWIZZLE_32B: rows of 32 bytes, 8-row atoms 256 bytes apart (layout type 6).  The leading byte offset is unused for
+// swizzled K-major operands whose K extent per instruction fits in one swizzle row (1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t atom_stride_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);           // start address, 16-byte units          bits [0,14)
     d |= (uint64_t)1 << 16;                                // leading byte offset (unused: 1)       bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset between 8-row atoms bits [32,46)
+    d |= (uint64_t)(atom_stride_bytes >> 4) << 32;         // stride byte offset between 8-row atoms bits [32,46)
     d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)        bits [46,48)
-    d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B              bits [61,64)
+    d |= (uint64_t)layout_type << 61;                      // layout type                           bits [61,64)
     return d;
 }
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) { return make_desc(smem_addr, 1024, 2); }
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr) { return make_desc(smem_addr, 256, 6); }
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128.
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
 // byte offset of 16-byte chunk `c` of row `r` inside a tile whose base is 1024-byte aligned (Swizzle<3,4,3>)
 __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+// same for a 32-byte-swizzled tile (Swizzle<1,4,3>: address bit 7 = bit 2 of the row, XORed into the chunk bit)
+__device__ __host__ __forceinline__ uint32_t sw32_offset(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
 
 }  // namespace tc
 
@@ -164,8 +178,7 @@ __global__ void __launch_bounds__(256) qdx_cells_tc_mean_kernel(const float* __r
 
 __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* __restrict__ cent, int64_t K, int32_t Dd,
                                                                    int64_t Kpad, const float* __restrict__ mu,
-                                                                   float* __restrict__ cs, float* __restrict__ cn,
-                                                                   float* __restrict__ cmax2) {
+                                                                   float* __restrict__ cs, float* __restrict__ cmax2) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kpad) return;
     float row[tc::KD];
@@ -177,11 +190,20 @@ __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* 
     }
     const int64_t tile = k / tc::TILE_N;
     const uint32_t r = (uint32_t)(k % tc::TILE_N);
-    char* base = (char*)cs + tile * tc::B_BYTES;
+    char* base = (char*)cs + tile * tc::STAGE_BYTES;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<float4*>(base + tc::sw128_offset(r, c)) = make_float4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
-    cn[k] = (k < K) ? n2 : INFINITY;
+    // -||c-mu||^2 / 2 as the exact sum of three floats with 11 significant bits each (what a TF32 operand keeps): the tensor
+    // core adds them to x . c against the ones of the A operand's extra columns
+    const float h = (k < K) ? -0.5f * n2 : tc::PAD_S;
+    const float h0 = __uint_as_float(__float_as_uint(h) & 0xFFFFE000u);
+    const float r1 = h - h0;
+    const float h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+    const float h2 = r1 - h1;
+    char* bx = base + tc::B_BYTES;
+    *reinterpret_cast<float4*>(bx + tc::sw32_offset(r, 0)) = make_float4(h0, h1, h2, 0.0f);
+    *reinterpret_cast<float4*>(bx + tc::sw32_offset(r, 1)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (k < K) atomicMax(reinterpret_cast<int*>(cmax2), __float_as_int(n2));     // n2 >= 0: int order == float order
 }
 
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(256) qdx_cells_tc_prepare_kernel(const float* 
 struct QdxTcParams {
     const float* desc; int64_t B; int32_t Dd;
     const float* cent; int64_t K; int64_t Kpad;
-    const float* cs; const float* cn; const float* cmax2; const float* mu;   // cmax2[0] = max ||c-mu||^2, mu = cmax2 + 32
+    const float* cs; const float* cmax2; const float* mu;   // cmax2[0] = max ||c-mu||^2, mu = cmax2 + 32
     int32_t* cells; int32_t* fallback_rows; int32_t* fallback_count;
     void* ws; const float* rep_f; const float* fit; int32_t offer; uint32_t idx_base; int32_t first_wins;
 };
@@ -212,8 +234,9 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* sA = smem;
-    uint8_t* sB = smem + A_BYTES;
-    uint64_t* bars = (uint64_t*)(smem + A_BYTES + STAGES * B_BYTES);
+    uint8_t* sAX = smem + A_BYTES;                 // extra K step of A: [1, 1, 1, 0, 0, 0, 0, 0] per row
+    uint8_t* sB = smem + A_BYTES + AX_BYTES;       // ring of centroid tiles: [16 KB SW128 block | 4 KB SW32 block] per stage
+    uint64_t* bars = (uint64_t*)(sB + STAGES * STAGE_BYTES);
     uint64_t* full = bars;                       // [STAGES]  copies landed
     uint64_t* empty = bars + STAGES;             // [STAGES]  MMA finished reading the stage
     uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES] accumulator ready
@@ -239,6 +262,10 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
         for (int j = 0; j < 4; ++j) { const int d = 4 * c + j; v[j] = (row < p.B && d < p.Dd) ? p.desc[row * p.Dd + d] - p.mu[d] : 0.0f; }
         *reinterpret_cast<float4*>(sA + sw128_offset(r, c)) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    for (int i = threadIdx.x; i < TILE_M * 2; i += NUM_THREADS) {
+        const int r = i >> 1, c = i & 1;
+        *reinterpret_cast<float4*>(sAX + sw32_offset(r, c)) = c == 0 ? make_float4(1.0f, 1.0f, 1.0f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -251,24 +278,26 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % STAGES; const uint32_t ph = (t / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], B_BYTES);
-                bulk_g2s(sB + s * B_BYTES, (const char*)p.cs + (int64_t)t * B_BYTES, B_BYTES, &full[s]);
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                bulk_g2s(sB + s * STAGE_BYTES, (const char*)p.cs + (int64_t)t * STAGE_BYTES, STAGE_BYTES, &full[s]);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint64_t desc_a = make_desc_sw128(smem_u32(sA));
+            const uint64_t desc_ax = make_desc_sw32(smem_u32(sAX));
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % STAGES; const uint32_t ph = (t / STAGES) & 1;
                 const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
                 mbar_wait(&acc_empty[a], aph ^ 1);
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t desc_b = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+                const uint64_t desc_b = make_desc_sw128(smem_u32(sB + s * STAGE_BYTES));
 #pragma unroll
                 for (int k = 0; k < KD / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 x 16 B
                     mma_tf32(tmem_base + a * TILE_N, desc_a + 2 * k, desc_b + 2 * k, IDESC, k > 0 ? 1u : 0u);
+                mma_tf32(tmem_base + a * TILE_N, desc_ax, make_desc_sw32(smem_u32(sB + s * STAGE_BYTES + B_BYTES)), IDESC, 1u);   // - ||c||^2 / 2
                 tc_commit(&empty[s]);        // frees the shared-memory stage once the MMAs have read it
                 tc_commit(&acc_full[a]);     // accumulator complete
             }
@@ -289,65 +318,56 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             finite = finite && (fabsf(xd) <= 3.40282347e+38f);
         }
         const float cm2 = *p.cmax2;
-        // band = 2*(error of d~ against the exact centred distance) + 2*(rounding error of the reference's float32 sum):
+        // band (in units of the distance d = ||x||^2 - 2 s) = 2*(error of d~ against the exact centred distance) + 2*(rounding
+        // error of the reference's float32 sum):
         //   TF32:       |d~ - d| <= 2 * 2^-9 * 1.02 * ||x-mu|| * max||c-mu||   (two truncated operands per product, Cauchy-Schwarz)
         //   centring:   fl(x-mu), fl(c-mu) are off by <= 2^-24 (|x|+|mu|) per component -> <= 2^-19 (||x||+||mu||+1)(max||c-mu||+||x-mu||+1)
         //   reference:  <= 40 * 2^-24 * (||x-mu|| + max||c-mu||)^2
+        // The tensor pass ranks s = x.c - ||c||^2/2 = (||x||^2 - d) / 2, so its band is half of that, plus the FP32 accumulation of
+        // the 40 products inside the tensor core (<= 2^-16 of the largest partial sum, generously); -||c||^2/2 itself enters exactly.
         const float xn = __fsqrt_rn(xn2), cmx = __fsqrt_rn(cm2);
-        const float band = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-18f * (__fsqrt_rn(xo2) + __fsqrt_rn(mu2) + 1.0f) * (cmx + xn + 1.0f)
-                         + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
-        float lv[TLIST]; int32_t lk[TLIST];
+        const float band_d = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-18f * (__fsqrt_rn(xo2) + __fsqrt_rn(mu2) + 1.0f) * (cmx + xn + 1.0f)
+                           + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
+        const float band = 0.5f * band_d + 0x1p-16f * (xn * cmx + 0.5f * cm2);
+        float lv[TLIST]; int32_t lk[TLIST];                  // candidates, DESCENDING in s
 #pragma unroll
-        for (int i = 0; i < TLIST; ++i) { lv[i] = INFINITY; lk[i] = 0x7fffffff; }
-        float thr = INFINITY;                              // admit d~ < thr = best + band (best = lv[0])
+        for (int i = 0; i < TLIST; ++i) { lv[i] = -INFINITY; lk[i] = 0x7fffffff; }
+        float thr = -INFINITY;                             // admit s~ > thr = best - band (best = lv[0])
 
-        // one 32-column chunk: d~ in place, branch-free running minimum; the (rare) admissible columns are then
-        // visited through a bit mask so the sorted insertion exists once in the instruction stream
-        auto process = [&](float (&acc)[32], const float4 (&cn)[8], int kbase) {
-            float m = INFINITY;
+        // one 32-column chunk: branch-free maximum (3-input FMNMX tree); the (rare) admissible columns are then visited
+        // through a bit mask so the sorted insertion exists once in the instruction stream
+        auto process = [&](float (&acc)[32], int kbase) {
+            float g[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float cnv[4] = {cn[q].x, cn[q].y, cn[q].z, cn[q].w};
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    acc[4 * q + jj] = __fmaf_rn(-2.0f, acc[4 * q + jj], cnv[jj]);
-                    m = fminf(m, acc[4 * q + jj]);
-                }
-            }
-            if (m < thr) {
+            for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(acc[4 * q], acc[4 * q + 1]), fmaxf(acc[4 * q + 2], acc[4 * q + 3]));
+            const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+            if (m > thr) {
                 uint32_t mask = 0;
 #pragma unroll
-                for (int jx = 0; jx < 32; ++jx) mask |= (acc[jx] < thr ? 1u : 0u) << jx;
+                for (int jx = 0; jx < 32; ++jx) mask |= (acc[jx] > thr ? 1u : 0u) << jx;
                 while (mask) {
                     const int jx = __ffs(mask) - 1; mask &= mask - 1;
                     float v = acc[0];
 #pragma unroll
                     for (int u = 1; u < 32; ++u) v = (jx == u) ? acc[u] : v;
-                    if (v < thr) {                          // thr may have tightened since the mask was built
+                    if (v > thr) {                          // thr may have tightened since the mask was built
                         int32_t kk = kbase + jx;
 #pragma unroll
-                        for (int u = 0; u < TLIST; ++u) {   // sorted insertion, ascending
-                            const bool sw = v < lv[u];
+                        for (int u = 0; u < TLIST; ++u) {   // sorted insertion, descending
+                            const bool sw = v > lv[u];
                             const float tv = sw ? lv[u] : v; const int32_t tk = sw ? lk[u] : kk;
                             lv[u] = sw ? v : lv[u]; lk[u] = sw ? kk : lk[u];
                             v = tv; kk = tk;
                         }
-                        thr = lv[0] + band;
+                        thr = lv[0] - band;
                     }
                 }
             }
         };
-        auto load_cn = [&](float4 (&cn)[8], int64_t col) {  // same addresses for every lane / epilogue warp: L1-resident
-            if (col >= p.Kpad) col = 0;
-            const float4* src = reinterpret_cast<const float4*>(p.cn + col);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cn[q] = __ldg(src + q);
-        };
 
-        // software pipeline over 32-column chunks (4 per tile, processed in ping-pong pairs): the TMEM load and the
-        // ||c-mu||^2 fetch of chunk i+1 are in flight while chunk i is processed
-        float accA[32], accB[32]; float4 cnA[8], cnB[8];
-        load_cn(cnA, 0);
+        // software pipeline over 32-column chunks (4 per tile, processed in ping-pong pairs): the TMEM load of chunk i+1 is in
+        // flight while chunk i is processed
+        float accA[32], accB[32];
         for (int t = 0; t < ntiles; ++t) {
             const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
             mbar_wait(&acc_full[a], aph);
@@ -359,12 +379,10 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             for (int c0 = 0; c0 < TILE_N; c0 += 64) {
                 tmem_wait_ld(accA);                                    // accA (chunk c0) has landed
                 tmem_ld32(taddr + c0 + 32, accB);                      // chunk c0+32 in flight
-                load_cn(cnB, (int64_t)kt + c0 + 32);
-                process(accA, cnA, kt + c0);
+                process(accA, kt + c0);
                 tmem_wait_ld(accB);                                    // accB has landed
                 if (c0 + 64 < TILE_N) tmem_ld32(taddr + c0 + 64, accA);
-                load_cn(cnA, (int64_t)kt + c0 + 64);                   // (first chunk of the next tile when c0 + 64 == TILE_N)
-                process(accB, cnB, kt + c0 + 32);
+                process(accB, kt + c0 + 32);
             }
             tc_fence_before();
             __syncwarp();
@@ -374,8 +392,8 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             int32_t cell = 0; bool resolved = true;
             if (finite) {
                 // every list entry within the final band is a candidate; a full list may have lost candidates
-                const float lim = lv[0] + band;
-                if (lv[TLIST - 1] <= lim) resolved = false;
+                const float lim = lv[0] - band;
+                if (lv[TLIST - 1] >= lim) resolved = false;
                 else {
                     float x[KD];
 #pragma unroll
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
                         float lvu = lv[0]; int32_t lku = lk[0];
 #pragma unroll
                         for (int w2 = 1; w2 < TLIST; ++w2) { lvu = (u == w2) ? lv[w2] : lvu; lku = (u == w2) ? lk[w2] : lku; }
-                        if (lvu <= lim && lku < p.K) {
+                        if (lvu >= lim && lku < p.K) {
                             const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)lku * p.Dd, p.Dd);
                             if (dex < best || (dex == best && lku < bk)) { best = dex; bk = lku; }
                         }
@@ -443,7 +461,7 @@ extern "C" {
 int qdx_cells_tc_workspace(int64_t K, int64_t B, int64_t* prep_floats, int64_t* scratch_ints) {
     if (K <= 0 || B < 0 || !prep_floats || !scratch_ints) return QDX_ERR_ARG;
     const int64_t Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
-    *prep_floats = Kpad * tc::KD + Kpad + 64;      // swizzled centred centroids | ||c-mu||^2 | [max ||c-mu||^2, pad x31, mu x32]
+    *prep_floats = Kpad * (tc::KD + tc::KX) + 64;  // per 128-centroid tile [swizzled centred centroids | -||c-mu||^2/2 block] | [max ||c-mu||^2, pad x31, mu x32]
     *scratch_ints = B + 64;                         // fallback rows | counter
     return 0;
 }
@@ -451,13 +469,13 @@ int qdx_cells_tc_workspace(int64_t K, int64_t B, int64_t* prep_floats, int64_t* 
 int qdx_cells_tc_prepare(const float* centroids, int64_t K, int32_t desc_dim, float* prep, void* stream) {
     if (!centroids || !prep || K <= 0 || desc_dim < 1 || desc_dim > tc::KD) return QDX_ERR_ARG;
     const int64_t Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
-    float* cs = prep; float* cn = prep + Kpad * tc::KD; float* cmax2 = cn + Kpad;
+    float* cs = prep; float* cmax2 = prep + Kpad * (tc::KD + tc::KX);
     cudaError_t e = cudaMemsetAsync(cmax2, 0, 64 * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     float* mu = cmax2 + 32;
     qdx_cells_tc_mean_kernel<<<tc::KD, 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, mu);
     QDX_CHECK_LAUNCH();
-    qdx_cells_tc_prepare_kernel<<<(unsigned)((Kpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, Kpad, mu, cs, cn, cmax2);
+    qdx_cells_tc_prepare_kernel<<<(unsigned)((Kpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(centroids, K, desc_dim, Kpad, mu, cs, cmax2);
     QDX_CHECK_LAUNCH();
     return 0;
 }
@@ -473,7 +491,7 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
     QdxTcParams p;
     p.desc = desc; p.B = B; p.Dd = desc_dim; p.cent = centroids; p.K = K;
     p.Kpad = (K + tc::TILE_N - 1) / tc::TILE_N * tc::TILE_N;
-    p.cs = prep; p.cn = prep + p.Kpad * tc::KD; p.cmax2 = p.cn + p.Kpad; p.mu = p.cmax2 + 32;
+    p.cs = prep; p.cmax2 = prep + p.Kpad * (tc::KD + tc::KX); p.mu = p.cmax2 + 32;
     p.cells = out_cells; p.fallback_rows = scratch; p.fallback_count = scratch + B;
     p.ws = ws; p.rep_f = rep_fitness; p.fit = fitness; p.offer = offer; p.idx_base = idx_base; p.first_wins = first_wins;
     cudaError_t e = cudaMemsetAsync(p.fallback_count, 0, sizeof(int32_t), st);
