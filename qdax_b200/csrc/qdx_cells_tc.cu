@@ -8,16 +8,16 @@
 //                    tcgen05.mma kind::tf32 (M=128, N=128), four K=8 steps over the 32 descriptor dimensions plus a FIFTH
 //                    K=8 step that multiplies [1, 1, 1, 0...] by [-||c||^2/2 split into three TF32-exact terms, 0...], so the
 //                    epilogue is a bare running maximum over the accumulator (no ||c||^2 fetch, no FMA per pair);
-//                    FP32 accumulators in TMEM, double buffered; centroid tiles stream through a 4-stage shared-memory
+//                    FP32 accumulators in TMEM, double buffered; centroid tiles stream through a 3-stage shared-memory
 //                    ring filled by ONE 1-D bulk async copy per tile (cp.async.bulk + mbarrier complete_tx) from a copy
 //                    of the centroids that was written ONCE in the layouts the UMMA descriptors expect: a 16 KB
 //                    128-byte-swizzled K-major block (a 32-float row is exactly one swizzle row, so no tensor map is
 //                    needed) followed by the 4 KB 32-byte-swizzled block of the extra K step; warp roles: 1 copy-issuer,
-//                    1 MMA-issuer, 4 epilogue warps (one TMEM lane quadrant each, thread = descriptor row).
+//                    1 MMA-issuer, 4 epilogue warps (one TMEM lane quadrant each, thread = descriptor row); two CTAs per SM.
 //                    Both x and c are centred on the centroid mean mu first (distances are translation invariant):
 //                    the TF32 error scales with ||x - mu|| * ||c - mu||, 4x smaller than the uncentred product for
 //                    data in [0,1]^32, and it makes the bound usable for tessellations far from the origin.
-//   2. candidates    every k with s~ >= max_k s~ - band_i is kept (sorted list of T), where band_i bounds twice the
+//   2. candidates    every 5-column group holding a k with s~ >= max_k s~ - band_i is recorded (row's slots in shared memory), where band_i bounds twice the
 //                    TF32 error (|x~c~ - xc| <= 2^-9 |xc| per product, Cauchy-Schwarz over the row) plus twice the
 //                    rounding error of the reference's own float32 sum -- so the list provably contains every index
 //                    that can attain the reference's computed minimum.
@@ -34,20 +34,31 @@
 namespace tc {
 
 constexpr int KD = 32;                 // padded descriptor dimension = one 128-byte swizzle row of float32
-constexpr int TILE_M = 128;            // descriptor rows per CTA (UMMA M)
+#ifndef QDX_TC_HALVES
+#define QDX_TC_HALVES 1                // 1 = 128 rows per CTA, two CTAs per SM; 2 = 256 rows per CTA sharing every centroid tile, one CTA per
+                                       // SM (half the L2 -> SM stream: measured 10 % SLOWER, the stream is 11 % of the L2 peak and two CTAs hide
+                                       // each other's accumulator hand-over latency; profiles/r2_notes.md)
+#endif
+constexpr int TILE_M = 128;            // descriptor rows per MMA (UMMA M)
+constexpr int HALVES = QDX_TC_HALVES;  // row tiles per CTA
+constexpr int CTA_ROWS = HALVES * TILE_M;
 constexpr int TILE_N = 128;            // centroids per MMA (UMMA N); 2 x 128 TMEM columns per CTA -> two CTAs per SM
-constexpr int STAGES = 4;              // shared-memory ring of centroid tiles
-constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (2 x 128 columns)
-constexpr int TMEM_COLS = ACC_STAGES * TILE_N;
-constexpr int TLIST = 16;              // candidates kept per row
+constexpr int STAGES = HALVES == 1 ? 3 : 6;   // shared-memory ring of centroid tiles (the copy warp runs ahead of the MMAs with 3 already)
+constexpr int ACC_STAGES = 2;          // TMEM accumulator double buffer (per stage: HALVES x 128 columns)
+constexpr int TMEM_COLS = ACC_STAGES * HALVES * TILE_N;
+constexpr int CAP = 16;                // recorded chunks per row (shared memory, append-only; compacted against the current threshold when full)
 constexpr int KX = 8;                  // the extra K step (one UMMA_K of tf32 = 32 bytes per row, SWIZZLE_32B)
 constexpr int A_BYTES = TILE_M * KD * 4;        // 16 KB
 constexpr int AX_BYTES = TILE_M * KX * 4;       // 4 KB
 constexpr int B_BYTES = TILE_N * KD * 4;        // 16 KB
 constexpr int BX_BYTES = TILE_N * KX * 4;       // 4 KB
 constexpr int STAGE_BYTES = B_BYTES + BX_BYTES; // one centroid tile: both blocks, contiguous in global memory too
-constexpr int NUM_THREADS = 192;       // warp 0: copies, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + AX_BYTES + STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int EPI_WARPS = 4 * HALVES;  // one per (row tile, TMEM lane quadrant)
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0: copies, warp 1: MMA + TMEM alloc, then the epilogue warps
+constexpr int CBUF_BYTES = CAP * CTA_ROWS * 8;
+constexpr int LIST_CAP = 48;           // centroid indices re-evaluated exactly per row at the end (list in the drained centroid ring)
+static_assert(LIST_CAP * CTA_ROWS * 4 <= STAGES * STAGE_BYTES, "the index lists reuse the centroid ring");
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + HALVES * A_BYTES + AX_BYTES + STAGES * STAGE_BYTES + 256 /*barriers*/ + CBUF_BYTES;
 constexpr float PAD_S = -1.0e30f;      // s of a padding centroid: never the maximum
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -229,32 +240,43 @@ __device__ __forceinline__ float qdx_exact_dist(const float (&x)[DDPAD], const f
     return acc;
 }
 
-__global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const QdxTcParams p) {
+// a row's slots are full: keep the recorded chunks whose maximum is still above the threshold (one copy in the instruction stream)
+__device__ __noinline__ int qdx_tc_compact(uint2* my, float thr) {
+    int w = 0;
+    for (int e = 0; e < tc::CAP; ++e) {
+        const uint2 x = my[e * tc::CTA_ROWS];
+        if (__uint_as_float(x.x) > thr) { my[w * tc::CTA_ROWS] = x; ++w; }
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(tc::NUM_THREADS, tc::HALVES == 1 ? 2 : 1) qdx_cells_tc_kernel(const QdxTcParams p) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* sA = smem;
-    uint8_t* sAX = smem + A_BYTES;                 // extra K step of A: [1, 1, 1, 0, 0, 0, 0, 0] per row
-    uint8_t* sB = smem + A_BYTES + AX_BYTES;       // ring of centroid tiles: [16 KB SW128 block | 4 KB SW32 block] per stage
+    uint8_t* sAX = smem + HALVES * A_BYTES;        // extra K step of A: [1, 1, 1, 0, 0, 0, 0, 0] per row (the same for every row tile)
+    uint8_t* sB = sAX + AX_BYTES;                  // ring of centroid tiles: [16 KB SW128 block | 4 KB SW32 block] per stage
     uint64_t* bars = (uint64_t*)(sB + STAGES * STAGE_BYTES);
     uint64_t* full = bars;                       // [STAGES]  copies landed
     uint64_t* empty = bars + STAGES;             // [STAGES]  MMA finished reading the stage
     uint64_t* acc_full = bars + 2 * STAGES;      // [ACC_STAGES] accumulator ready
     uint64_t* acc_empty = bars + 2 * STAGES + ACC_STAGES;   // [ACC_STAGES] accumulator drained by the epilogue
     uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * STAGES + 2 * ACC_STAGES);
+    uint2* cbuf = (uint2*)((uint8_t*)bars + 256);          // [CAP][CTA_ROWS] (s~ bits, centroid index): entry-major, lanes side by side
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+    const int64_t row0 = (int64_t)blockIdx.x * CTA_ROWS;
     const int ntiles = (int)(p.Kpad / TILE_N);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }   // 4 epilogue warps
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
     // A tile: 128 descriptor rows, zero-padded to 32 floats, written in the swizzled layout by all threads
-    for (int i = threadIdx.x; i < TILE_M * 8; i += NUM_THREADS) {
+    for (int i = threadIdx.x; i < CTA_ROWS * 8; i += NUM_THREADS) {     // row tile h at sA + h * A_BYTES (r * 128 bytes per row: contiguous)
         const int r = i >> 3, c = i & 7;
         const int64_t row = row0 + r;
         float v[4];
@@ -285,7 +307,6 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint64_t desc_a = make_desc_sw128(smem_u32(sA));
             const uint64_t desc_ax = make_desc_sw32(smem_u32(sAX));
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % STAGES; const uint32_t ph = (t / STAGES) & 1;
@@ -294,18 +315,24 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint64_t desc_b = make_desc_sw128(smem_u32(sB + s * STAGE_BYTES));
+                const uint64_t desc_bx = make_desc_sw32(smem_u32(sB + s * STAGE_BYTES + B_BYTES));
 #pragma unroll
-                for (int k = 0; k < KD / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 x 16 B
-                    mma_tf32(tmem_base + a * TILE_N, desc_a + 2 * k, desc_b + 2 * k, IDESC, k > 0 ? 1u : 0u);
-                mma_tf32(tmem_base + a * TILE_N, desc_ax, make_desc_sw32(smem_u32(sB + s * STAGE_BYTES + B_BYTES)), IDESC, 1u);   // - ||c||^2 / 2
+                for (int h = 0; h < HALVES; ++h) {
+                    const uint64_t desc_a = make_desc_sw128(smem_u32(sA + h * A_BYTES));
+                    const uint32_t tacc = tmem_base + (uint32_t)((a * HALVES + h) * TILE_N);
+#pragma unroll
+                    for (int k = 0; k < KD / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 x 16 B
+                        mma_tf32(tacc, desc_a + 2 * k, desc_b + 2 * k, IDESC, k > 0 ? 1u : 0u);
+                    mma_tf32(tacc, desc_ax, desc_bx, IDESC, 1u);   // - ||c||^2 / 2
+                }
                 tc_commit(&empty[s]);        // frees the shared-memory stage once the MMAs have read it
                 tc_commit(&acc_full[a]);     // accumulator complete
             }
         }
     } else {
         // ===== epilogue: thread = descriptor row; warp w may only touch TMEM lanes 32*(w%4) .. +31 =====
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int r = half * TILE_M + quad * 32 + lane;
         const int64_t row = row0 + r;
         const bool valid = row < p.B;
         float xn2 = 0.0f, xo2 = 0.0f, mu2 = 0.0f; bool finite = true;
@@ -329,39 +356,45 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
         const float band_d = 2.0f * (1.02f * 0x1p-8f * xn * cmx) + 0x1p-18f * (__fsqrt_rn(xo2) + __fsqrt_rn(mu2) + 1.0f) * (cmx + xn + 1.0f)
                            + 0x1p-17f * (xn + cmx) * (xn + cmx) + 1e-30f;
         const float band = 0.5f * band_d + 0x1p-16f * (xn * cmx + 0.5f * cm2);
-        float lv[TLIST]; int32_t lk[TLIST];                  // candidates, DESCENDING in s
-#pragma unroll
-        for (int i = 0; i < TLIST; ++i) { lv[i] = -INFINITY; lk[i] = 0x7fffffff; }
-        float thr = -INFINITY;                             // admit s~ > thr = best - band (best = lv[0])
-
-        // one 32-column chunk: branch-free maximum (3-input FMNMX tree); the (rare) admissible columns are then visited
-        // through a bit mask so the sorted insertion exists once in the instruction stream
+        // A chunk with an admissible column is RECORDED in the row's slots in shared memory -- one 8-byte store of (chunk maximum,
+        // chunk id, bit per column group that holds an admissible column) -- and the recorded groups are re-evaluated exactly at the
+        // end.  Measured alternatives (r2_notes.md): a sorted register list of candidates costs a 16-level compare / select chain
+        // per admission plus a 32-way register select, executed by the whole warp for one lane on the path that hands the
+        // accumulator back to the MMA warp (half of the kernel's time); appending the columns themselves needs one store site per
+        // column and unrolled copy, 7.9 k instructions, and stalls on instruction fetch.
+        uint2* const my = cbuf + r;                        // slot e of this row: my[e * CTA_ROWS]
+        int cnt = 0; bool lost = false;
+        float best = -INFINITY, thr = -INFINITY;           // admit s~ > thr = best - band
+        // One 32-column chunk.  Hot path: 16 three-input maxima (six groups of five columns, one of two) and one compare.
+        // An admissible column turns up in ~10 % of the chunks for SOME lane of the warp (each row sees ~ln(chunks) running-maximum
+        // records plus its band neighbours): the lane raises its threshold to the new maximum first, then records the chunk.
         auto process = [&](float (&acc)[32], int kbase) {
-            float g[8];
+#ifdef QDX_TC_DEBUG_LD_ONLY       // timing experiment: TMEM reads only (results wrong)
+            if (acc[0] == 1.2345e37f) thr = acc[1];
+            return;
+#endif
+#define QDX_MX3(a_, b_, c_) fmaxf(fmaxf((a_), (b_)), (c_))
+            float g[7];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) g[q] = fmaxf(fmaxf(acc[4 * q], acc[4 * q + 1]), fmaxf(acc[4 * q + 2], acc[4 * q + 3]));
-            const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+            for (int q = 0; q < 6; ++q) g[q] = QDX_MX3(QDX_MX3(acc[5 * q], acc[5 * q + 1], acc[5 * q + 2]), acc[5 * q + 3], acc[5 * q + 4]);
+            g[6] = fmaxf(acc[30], acc[31]);
+            const float m = QDX_MX3(QDX_MX3(g[0], g[1], g[2]), QDX_MX3(g[3], g[4], g[5]), g[6]);
+#undef QDX_MX3
+#ifdef QDX_TC_DEBUG_HOT_ONLY      // timing experiment: hot path only (results wrong)
+            if (m > 1e37f) {
+#else
             if (m > thr) {
-                uint32_t mask = 0;
+#endif
+                if (m > best) { best = m; thr = best - band; }
+                uint32_t gm = 0;
 #pragma unroll
-                for (int jx = 0; jx < 32; ++jx) mask |= (acc[jx] > thr ? 1u : 0u) << jx;
-                while (mask) {
-                    const int jx = __ffs(mask) - 1; mask &= mask - 1;
-                    float v = acc[0];
-#pragma unroll
-                    for (int u = 1; u < 32; ++u) v = (jx == u) ? acc[u] : v;
-                    if (v > thr) {                          // thr may have tightened since the mask was built
-                        int32_t kk = kbase + jx;
-#pragma unroll
-                        for (int u = 0; u < TLIST; ++u) {   // sorted insertion, descending
-                            const bool sw = v > lv[u];
-                            const float tv = sw ? lv[u] : v; const int32_t tk = sw ? lk[u] : kk;
-                            lv[u] = sw ? v : lv[u]; lk[u] = sw ? kk : lk[u];
-                            v = tv; kk = tk;
-                        }
-                        thr = lv[0] - band;
-                    }
+                for (int q = 0; q < 7; ++q) gm |= (g[q] > thr ? 1u : 0u) << q;
+                if (cnt == CAP) {                          // full: drop the chunks the threshold has overtaken since they were recorded
+                    cnt = qdx_tc_compact(my, thr);
+                    if (cnt == CAP) { lost = true; cnt = CAP - 1; }      // more than CAP chunks inside the band: exact fallback for this row
                 }
+                my[cnt * CTA_ROWS] = make_uint2(__float_as_uint(m), ((uint32_t)kbase << 2) | gm);     // kbase is a multiple of 32: (chunk id << 7) | groups
+                ++cnt;
             }
         };
 
@@ -372,7 +405,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
             const int a = t % ACC_STAGES; const uint32_t aph = (t / ACC_STAGES) & 1;
             mbar_wait(&acc_full[a], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * TILE_N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((a * HALVES + half) * TILE_N);
             const int kt = t * TILE_N;
             tmem_ld32(taddr, accA);
 #pragma unroll
@@ -391,28 +424,49 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 2) qdx_cells_tc_kernel(const 
         if (valid) {
             int32_t cell = 0; bool resolved = true;
             if (finite) {
-                // every list entry within the final band is a candidate; a full list may have lost candidates
-                const float lim = lv[0] - band;
-                if (lv[TLIST - 1] >= lim) resolved = false;
+                // every appended entry within the final band is a candidate; a row that overflowed its slots may have lost some
+                if (lost || cnt == 0) resolved = false;
                 else {
+                    const float lim = best - band;
+                    // flatten the recorded groups that survive the final band into a per-row list of centroid indices first (in
+                    // the centroid ring: every copy has landed and every MMA has completed once this warp has seen the last
+                    // accumulator), so that the lanes of the warp walk their lists in step -- evaluating straight out of the
+                    // slots had each lane's one or two survivors at different slot / group positions and the warp paid for ~150
+                    // exact distances instead of ~10 (r2_notes.md)
+                    int32_t* const lst = reinterpret_cast<int32_t*>(sB) + r;       // element i of this row: lst[i * CTA_ROWS]
+                    int n = 0;
+#pragma unroll 1
+                    for (int e = 0; e < cnt; ++e) {
+                        const uint2 c = my[e * CTA_ROWS];
+                        if (!(__uint_as_float(c.x) >= lim)) continue;          // overtaken by a later maximum
+                        const int32_t k0 = (int32_t)(c.y >> 7) << 5;
+#pragma unroll 1
+                        for (int q = 0; q < 7; ++q) {
+                            if (!((c.y >> q) & 1u)) continue;
+                            const int32_t ke = min(k0 + (q < 6 ? 5 * q + 5 : 32), (int32_t)p.K);
+                            for (int32_t ck = k0 + 5 * q; ck < ke; ++ck) {
+                                if (n < LIST_CAP) { lst[n * CTA_ROWS] = ck; ++n; } else lost = true;
+                            }
+                        }
+                    }
                     float x[KD];
 #pragma unroll
                     for (int d = 0; d < KD; ++d) x[d] = d < p.Dd ? p.desc[row * p.Dd + d] : 0.0f;
-                    float best = INFINITY; int32_t bk = 0x7fffffff;
+                    float dbest = INFINITY; int32_t bk = 0x7fffffff;
 #pragma unroll 1
-                    for (int u = 0; u < TLIST; ++u) {
-                        float lvu = lv[0]; int32_t lku = lk[0];
-#pragma unroll
-                        for (int w2 = 1; w2 < TLIST; ++w2) { lvu = (u == w2) ? lv[w2] : lvu; lku = (u == w2) ? lk[w2] : lku; }
-                        if (lvu >= lim && lku < p.K) {
-                            const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)lku * p.Dd, p.Dd);
-                            if (dex < best || (dex == best && lku < bk)) { best = dex; bk = lku; }
-                        }
+                    for (int i = 0; i < n; ++i) {                               // the reference expression on every column of a recorded group
+                        const int32_t ck = lst[i * CTA_ROWS];
+                        const float dex = qdx_exact_dist<KD>(x, p.cent + (int64_t)ck * p.Dd, p.Dd);
+                        if (dex < dbest || (dex == dbest && ck < bk)) { dbest = dex; bk = ck; }
                     }
+                    if (lost) bk = 0x7fffffff;
                     if (bk == 0x7fffffff) resolved = false; else cell = bk;
                 }
             }
             // non-finite descriptor: every distance is inf or NaN -> first index (centroids are finite)
+#if defined(QDX_TC_DEBUG_LD_ONLY) || defined(QDX_TC_DEBUG_HOT_ONLY)
+            resolved = true;
+#endif
             if (resolved) {
                 p.cells[row] = cell;
                 if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
@@ -498,7 +552,7 @@ int qdx_cells_tc(const float* desc, int64_t B, int32_t desc_dim, const float* ce
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(qdx_cells_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    qdx_cells_tc_kernel<<<(unsigned)((B + tc::TILE_M - 1) / tc::TILE_M), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p);
+    qdx_cells_tc_kernel<<<(unsigned)((B + tc::CTA_ROWS - 1) / tc::CTA_ROWS), tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p);
     QDX_CHECK_LAUNCH();
     qdx_cells_tc_fallback_kernel<<<148, 128, 0, st>>>(p);
     QDX_CHECK_LAUNCH();
