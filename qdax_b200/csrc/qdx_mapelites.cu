@@ -1191,6 +1191,11 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) 
 //   persistent, dynamic, guided (tiles shrinking from 32 to 8 rows)             100.9 / 179.4 / 676 us   (row-serial scoring phase costs the same for 8 rows as for 32)
 //   persistent, dynamic, equal tiles of 28 rows (whole tiles per warp)           96.0 / 203.1 / 674 us
 //   persistent, dynamic, 32-row tiles                                            this build
+//   same + end game: once less than one round of tiles is left, pieces of 8 / 16 rows fill a warp's 32-row tile before ONE
+//   scoring pass (round 2, gpurun_out/r2r_gen_*.json)                           110.2 / 193.0 / 688 us (8 rows), 100.0 / 182.9 / 686 (16)
+//                                                                          vs    98.6 / 176.9 / 680 us without, same run: the finer
+//   deal does not shorten the tail -- what is left at the end runs on SM sub-partitions with one or two warps, at their
+//   latency-bound single-warp rate, however it is cut -- and pays a lane = row parent-selection pass per piece.
 // The tail of the kernel is the lowest-priority warp of every SM sub-partition finishing its last tile alone, at
 // single-warp issue rate; smaller last tiles shorten it but pay the fixed per-tile cost of the lane = row scoring phase.
 static int32_t generate_tile_rows(int64_t, unsigned) { return 32; }
