@@ -17,6 +17,7 @@
 // qdax/core/emitters/mutation_operators.py:175-226, qdax/tasks/arm.py:9-50,
 // qdax/tasks/standard_functions.py:9-48, qdax/core/containers/mapelites_repertoire.py:111-266,
 // qdax/utils/metrics.py:74-98.
+#include <cstdlib>
 #include "qdx_common.cuh"
 #include "qdx_cells_index.cuh"
 #include "../../include/qdx.h"
@@ -1153,8 +1154,9 @@ static int fill_grid(const qdx_grid_desc* gd, int32_t desc_dim, QdxGrid* g) {
 
 // Grid of the generate kernel: ceil(B / 128) CTAs, capped at ONE resident wave (SMs x CTAs per SM for this instantiation and
 // this much dynamic shared memory): the kernel is persistent, warp w owns rows [B w / W, B (w + 1) / W).
+static int32_t generate_tile_rows(int64_t, unsigned);
 template <typename Kern>
-static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) {
+static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out, int32_t* tile_rows_out) {
     // (kernel, shared memory, device) -> resident CTAs: queried once, then served from a small table (the attribute call and
     // the occupancy query cost microseconds each, on a path that enqueues a 100 us generation)
     struct Entry { const void* k; size_t smem; int dev; int64_t cap; };
@@ -1180,8 +1182,16 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out) 
         cap = (int64_t)sms * per_sm;
         if (n_entries < 128) table[n_entries++] = Entry{(const void*)kern, smem, dev, cap};     // (a benign race: worst case an entry is queried twice)
     }
-    const int64_t g = (B + QDX_GEN_WARPS * 32 - 1) / (QDX_GEN_WARPS * 32);
+    // Small batches (fewer rows than 16 per resident warp: the README-sized runs) are latency problems: a warp walks its tile
+    // alone on its SM sub-partition, so the rows are spread over more warps in tiles of 8 or 16 (QDX_GEN_SMALL_TILES=0: off).
+    static int small_tiles = -1;
+    if (small_tiles < 0) { const char* e_ = getenv("QDX_GEN_SMALL_TILES"); small_tiles = e_ ? atoi(e_) : 1; }
+    int32_t tile_rows = generate_tile_rows(B, 0);
+    const int64_t per_warp = (B + cap * QDX_GEN_WARPS - 1) / (cap * QDX_GEN_WARPS);
+    if (small_tiles && per_warp <= 16) tile_rows = per_warp <= 8 ? 8 : 16;
+    const int64_t g = (B + QDX_GEN_WARPS * tile_rows - 1) / (QDX_GEN_WARPS * tile_rows);
     *grid_out = (unsigned)(g < cap ? g : cap);
+    *tile_rows_out = tile_rows;
     return 0;
 }
 
@@ -1205,9 +1215,10 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
 #define QDX_LAUNCH_GEN(GD)                                                                                         \
     do {                                                                                                           \
         unsigned g_ = 0;                                                                                           \
-        int rc_ = generate_grid(qdx_generate_kernel<TASK, GD, ARM_CLIP>, smem, p.B, &g_);                          \
+        int32_t tr_ = 32;                                                                                          \
+        int rc_ = generate_grid(qdx_generate_kernel<TASK, GD, ARM_CLIP>, smem, p.B, &g_, &tr_);                    \
         if (rc_) return rc_;                                                                                       \
-        QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);                                           \
+        QdxGenParams q_ = p; q_.tile_rows = tr_;                                                                   \
         cudaError_t e_ = qdx_launch_pdl(qdx_generate_kernel<TASK, GD, ARM_CLIP>, dim3(g_), dim3(QDX_GEN_WARPS * 32), smem, st, q_); \
         if (e_ != cudaSuccess) return (int)e_;                                                                     \
     } while (0)
@@ -1222,9 +1233,10 @@ static int launch_generate_task(const QdxGenParams& p, size_t smem, cudaStream_t
     } else if (TASK == QDX_TASK_NONE) {
         if (p.leaves.n > 1) {
             unsigned g_ = 0;
-            int rc_ = generate_grid(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, smem, p.B, &g_);
+            int32_t tr_ = 32;
+            int rc_ = generate_grid(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, smem, p.B, &g_, &tr_);
             if (rc_) return rc_;
-            QdxGenParams q_ = p; q_.tile_rows = generate_tile_rows(p.B, g_);
+            QdxGenParams q_ = p; q_.tile_rows = tr_;
             cudaError_t e_ = qdx_launch_pdl(qdx_generate_kernel<QDX_TASK_NONE, 0, false, true>, dim3(g_), dim3(QDX_GEN_WARPS * 32), smem, st, q_);
             if (e_ != cudaSuccess) return (int)e_;
         } else {
