@@ -73,20 +73,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-#ifndef QDX_TC_WAIT_HINT
-#define QDX_TC_WAIT_HINT 0    // EXPERIMENT for round 2 (compiled, not yet run): suspend-time hint in ns for the mbarrier waits -- a third
-#endif                        // of the issued instructions of the v3 kernel are try_wait spins of the copy / MMA warps (r1_notes.md)
+// (a suspend-time hint on try_wait was measured in round 2: 1.0646 vs 1.0661 ms, no effect -- profiles/r2_notes.md)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if QDX_TC_WAIT_HINT
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)QDX_TC_WAIT_HINT) : "memory");
-#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
@@ -95,7 +83,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-#endif
 }
 // ---- bulk async copy global -> shared, completion on an mbarrier ----------------------------------------------
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -369,10 +356,6 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, tc::HALVES == 1 ? 2 : 1) qdx_
         // An admissible column turns up in ~10 % of the chunks for SOME lane of the warp (each row sees ~ln(chunks) running-maximum
         // records plus its band neighbours): the lane raises its threshold to the new maximum first, then records the chunk.
         auto process = [&](float (&acc)[32], int kbase) {
-#ifdef QDX_TC_DEBUG_LD_ONLY       // timing experiment: TMEM reads only (results wrong)
-            if (acc[0] == 1.2345e37f) thr = acc[1];
-            return;
-#endif
 #define QDX_MX3(a_, b_, c_) fmaxf(fmaxf((a_), (b_)), (c_))
             float g[7];
 #pragma unroll
@@ -380,11 +363,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, tc::HALVES == 1 ? 2 : 1) qdx_
             g[6] = fmaxf(acc[30], acc[31]);
             const float m = QDX_MX3(QDX_MX3(g[0], g[1], g[2]), QDX_MX3(g[3], g[4], g[5]), g[6]);
 #undef QDX_MX3
-#ifdef QDX_TC_DEBUG_HOT_ONLY      // timing experiment: hot path only (results wrong)
-            if (m > 1e37f) {
-#else
             if (m > thr) {
-#endif
                 if (m > best) { best = m; thr = best - band; }
                 uint32_t gm = 0;
 #pragma unroll
@@ -464,9 +443,6 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, tc::HALVES == 1 ? 2 : 1) qdx_
                 }
             }
             // non-finite descriptor: every distance is inf or NaN -> first index (centroids are finite)
-#if defined(QDX_TC_DEBUG_LD_ONLY) || defined(QDX_TC_DEBUG_HOT_ONLY)
-            resolved = true;
-#endif
             if (resolved) {
                 p.cells[row] = cell;
                 if (p.offer) qdx_offer(p.ws, p.K, p.rep_f, cell, p.fit[row], p.idx_base + (uint32_t)row, p.first_wins);
