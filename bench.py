@@ -435,7 +435,7 @@ def kernel_rooflines(cfg, name, kern_ms, B, K, world, clocks_mhz, W):
     if "commit" in kern_ms:
         t = kern_ms["commit"] * 1e-3
         cb = K * ab["commit_fixed_per_cell"] + W * ab["commit_per_winner"]
-        out["commit"] = {"kernel": "qdx_commit_stream_kernel", "bound": "hbm", "achieved": cb / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        out["commit"] = {"kernel": "qdx_commit_lean_kernel" if D <= 256 else "qdx_commit_stream_kernel", "bound": "hbm", "achieved": cb / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": cb / t / 1e9 / hbm_peak, "winners_last_step": W, "algorithmic_bytes_per_launch": cb, "avg_launch_ms": kern_ms["commit"],
                          "note": "launch / latency bound whenever W * row bytes is small (SURVEY.md 8d caveat); see insert_roofline.large_rows"}
     return out
@@ -661,9 +661,14 @@ def run_gpu(args, cfg):
                         "only the offspring rows reach DRAM" % (rl[dom]["bound"], dom)}
     insert = dict(rl.get("commit", {}))
     if world == 1 and not args.no_insert_probe:
+        # the insert kernel's HBM roofline is only meaningful where W * row bytes is large: the headline figure is
+        # the SUSTAINED one of the 4 KB-row probe (train of 8 back-to-back launches); the timed workload's own commit sits beside it
         probe = insert_probe(dev, hbm_peak)
-        insert["large_rows"] = probe
-        insert["headline"] = {"frac": probe["train_of_8_frac"], "what": "train of 8 back-to-back launches at 4 KB rows (sustained), of measured HBM copy peak"}
+        insert = {"kernel": "qdx_commit_stream_kernel", "bound": "hbm", "achieved": probe["train_of_8_achieved"], "peak": hbm_peak, "unit": "GB/s",
+                  "frac": probe["train_of_8_frac"], "what": "train of 8 back-to-back launches at 4 KB rows (sustained), of the measured HBM copy peak",
+                  "single_launch_frac": probe["frac"], "traffic": probe["traffic"], "large_rows": probe,
+                  "headline": {"frac": probe["train_of_8_frac"], "what": "train of 8 back-to-back launches at 4 KB rows (sustained), of measured HBM copy peak"},
+                  "timed_workload_commit": rl.get("commit", {})}
 
     others = None
     if world == 1 and not args.no_other_configs:
