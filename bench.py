@@ -595,8 +595,8 @@ def run_gpu(args, cfg):
     value = args.steps * B_total / (ms_total * 1e-3)
 
     # ---- e2e: the same public call + the step's metrics read back to the host, inside the timed region -------------
-    # "pipelined" copies every step's metrics to PINNED host memory with an async D2H + event and consumes them one step
-    # behind (what a loop that logs metrics does); "blocking" calls .cpu() on the metrics after every step.
+    # "pipelined" has every step's metrics written to PINNED host memory by the commit kernel itself (update(..., metrics_out=
+    # pinned slot)) + an event, and consumes them one step behind (what a loop that logs metrics does); "blocking" calls .cpu() on the metrics after every step.
     e2e_steps = args.steps
     pinned = torch.empty((2, 4), dtype=torch.float32).pin_memory()
     evs = [torch.cuda.Event(), torch.cuda.Event()]
@@ -608,11 +608,13 @@ def run_gpu(args, cfg):
         for s_i in range(e2e_steps):
             ks = qr.split(key)                                    # host-side key chain, README.md:133
             key, sub = ks[0], ks[1]
-            rep, state, md = me.update(rep, state, sub, donate=True)
             if mode == "blocking":
+                rep, state, md = me.update(rep, state, sub, donate=True)
                 host_metrics = me._last_metrics.cpu()             # D2H of the step's metrics (16 B) + sync every step
             else:
-                pinned[s_i & 1].copy_(me._last_metrics, non_blocking=True)
+                # the commit kernel writes the step's metrics straight into the pinned host slot (16 B over PCIe, no copy node
+                # between this generation's commit and the next generation's generate); the event orders the host's read
+                rep, state, md = me.update(rep, state, sub, donate=True, metrics_out=pinned[s_i & 1])
                 evs[s_i & 1].record()
                 if s_i > 0:
                     evs[(s_i - 1) & 1].synchronize()
@@ -692,7 +694,7 @@ def run_gpu(args, cfg):
         "timed_api": ("MAPElites.update" if world == 1 else "DistributedMAPElites.update") + "(repertoire, emitter_state, key, donate=True), host key chain",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / e2e_steps,
                 "api": ("MAPElites.update(repertoire, emitter_state, key, donate=True)" if world == 1 else "DistributedMAPElites.update(...) per rank")
-                       + " + every step's metrics copied to pinned host memory (async D2H + event) and read one step behind",
+                       + " + every step's metrics written by the commit kernel to pinned host memory (metrics_out=, 16 B over PCIe, + event) and read one step behind",
                 "blocking_readback_value": e2e_blocking_value,
                 "note": "inputs of a step are the 2-word RNG key (host) and the HBM-resident repertoire (carried state)"},
         "insertions": {"per_s": inserted / (ms_total * 1e-3), "per_step": inserted / args.steps,

@@ -40,7 +40,7 @@ from qdax_b200 import _native, parallel
 from qdax_b200 import random as qrandom
 from qdax_b200.core.containers.mapelites_repertoire import MapElitesRepertoire
 from qdax_b200.core.emitters.emitter import EmitterState
-from qdax_b200.core.map_elites import MAPElites
+from qdax_b200.core.map_elites import MAPElites, _metrics_destination
 
 
 class DistributedMAPElites(MAPElites):
@@ -182,7 +182,8 @@ class DistributedMAPElites(MAPElites):
                        metrics_out=metrics_out, mode=2)
         self._mark("commit")
 
-    def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False):
+    def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False,
+               metrics_out: Optional[torch.Tensor] = None):
         """reference :92-161.  `key` is this rank's key (examples/distributed_mapelites.ipynb cell 23:
         keys = split(key, num_devices))."""
         if self._scoring_function is None:
@@ -190,7 +191,7 @@ class DistributedMAPElites(MAPElites):
         cfg = self._fused_config(repertoire)
         if cfg is not None:
             rep = repertoire if donate else repertoire._clone_state()
-            m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
+            m = _metrics_destination(metrics_out, rep.genotypes.device)
             self._fused_distributed_generation(rep, cfg, _native.KEYMODE_DIST_UPDATE, key, m)
             self._last_metrics = m
             return rep, emitter_state, self._metrics_dict(m)

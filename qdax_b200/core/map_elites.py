@@ -53,6 +53,19 @@ def _qd_offset_of(metrics_function) -> Optional[float]:
     return None
 
 
+def _metrics_destination(metrics_out: Optional[torch.Tensor], device) -> torch.Tensor:
+    """Where the commit kernel writes (qd_score, max_fitness, coverage, inserted): a fresh device tensor, or the caller's -- a
+    device tensor, or a PINNED host tensor, which the kernel then writes straight over PCIe (the device -> host transfer of a
+    logging loop without a copy node in the stream: order the read with an event recorded after the call)."""
+    if metrics_out is None:
+        return torch.empty(4, dtype=torch.float32, device=device)
+    if metrics_out.dtype != torch.float32 or metrics_out.numel() != 4 or not metrics_out.is_contiguous():
+        raise ValueError("metrics_out must be a contiguous float32 tensor of 4 elements")
+    if not (metrics_out.is_cuda and metrics_out.device == device) and not (metrics_out.device.type == "cpu" and metrics_out.is_pinned()):
+        raise ValueError("metrics_out must live on the repertoire's device or in pinned host memory")
+    return metrics_out
+
+
 class MAPElites:
     """Core elements of the MAP-Elites algorithm (reference :22-55)."""
 
@@ -197,15 +210,17 @@ class MAPElites:
         metrics = self._metrics_function(repertoire)
         return repertoire, emitter_state, metrics
 
-    def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False):
+    def update(self, repertoire: MapElitesRepertoire, emitter_state: Optional[EmitterState], key, *, donate: bool = False,
+               metrics_out: Optional[torch.Tensor] = None):
         """One MAP-Elites iteration (reference :148-195).  `donate=True` updates the repertoire's buffers in
-        place (jax buffer donation); by default the input repertoire is left untouched."""
+        place (jax buffer donation); by default the input repertoire is left untouched.  `metrics_out` (fused path only):
+        see `_metrics_destination`."""
         if self._scoring_function is None:
             raise ValueError("Scoring function is not set.")
         cfg = self._fused_config(repertoire)
         if cfg is not None:
             rep = repertoire if donate else repertoire._clone_state()
-            m = torch.empty(4, dtype=torch.float32, device=rep.genotypes.device)
+            m = _metrics_destination(metrics_out, rep.genotypes.device)
             self._fused_generation(rep, cfg, _native.KEYMODE_UPDATE, key, m)
             self._last_metrics = m          # (qd_score, max_fitness, coverage, inserted) as one device tensor
             return rep, emitter_state, self._metrics_dict(m)

@@ -701,3 +701,40 @@ def test_dns_golden_and_random(dev, golden, co):
     G, F, Dn, meta, surv = co.dns_add(pg, np.ones(P, np.float32), np.full((P, 2), 0.5, np.float32), bg, np.ones(B, np.float32), np.full((B, 2), 0.5, np.float32), 3)
     out = _native.dns_add(T(pg, dev), T(np.ones(P), dev), T(np.full((P, 2), 0.5), dev), T(bg, dev), T(np.ones(B), dev), T(np.full((B, 2), 0.5), dev), 3)
     assert np.array_equal(N(out[3]), meta, equal_nan=True) and np.array_equal(N(out[4]), surv) and np.array_equal(N(out[0]), G)
+
+
+def test_update_metrics_into_pinned_host_memory(dev):
+    """MAPElites.update(..., metrics_out=<pinned host tensor>): the commit kernel writes the step's metrics straight into
+    host memory (what bench.py's pipelined e2e loop reads); same values as the device-side metrics of an identical run."""
+    from qdax_b200 import random as qr
+    from qdax_b200.core.containers.mapelites_repertoire import compute_euclidean_centroids
+    from qdax_b200.core.emitters.mutation_operators import isoline_variation
+    from qdax_b200.core.emitters.standard_emitters import MixingEmitter
+    from qdax_b200.core.map_elites import MAPElites
+    from qdax_b200.tasks.arm import arm_scoring_function
+    from qdax_b200.utils.metrics import default_qd_metrics
+
+    def run(pinned):
+        em = MixingEmitter(lambda x, k: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, 512)
+        me = MAPElites(arm_scoring_function, em, functools.partial(default_qd_metrics, qd_offset=0.0))
+        cent = compute_euclidean_centroids((16, 16), 0.0, 1.0, device=dev)
+        rep, state, _ = me.init(qr.uniform(qr.key(1), (64, 12), device=dev), cent, qr.key(2))
+        key, out = qr.key(3), []
+        for s in range(4):
+            ks = qr.split(key)
+            key, sub = ks[0], ks[1]
+            if pinned is None:
+                rep, state, md = me.update(rep, state, sub, donate=True)
+                out.append(me._last_metrics.cpu().numpy().copy())
+            else:
+                rep, state, md = me.update(rep, state, sub, donate=True, metrics_out=pinned[s & 1])
+                torch.cuda.synchronize()
+                out.append(pinned[s & 1].numpy().copy())
+        return np.stack(out), N(rep.fitnesses)
+
+    pinned = torch.zeros((2, 4), dtype=torch.float32).pin_memory()
+    a, fa = run(None)
+    b, fb = run(pinned)
+    assert np.array_equal(a, b) and np.array_equal(fa, fb)
+    with pytest.raises(ValueError):
+        run(torch.zeros((2, 4), dtype=torch.float32))          # pageable host memory is refused
