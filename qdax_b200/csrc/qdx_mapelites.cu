@@ -1182,13 +1182,14 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out, 
         cap = (int64_t)sms * per_sm;
         if (n_entries < 128) table[n_entries++] = Entry{(const void*)kern, smem, dev, cap};     // (a benign race: worst case an entry is queried twice)
     }
-    // Small batches (fewer rows than 16 per resident warp: the README-sized runs) are latency problems: a warp walks its tile
-    // alone on its SM sub-partition, so the rows are spread over more warps in tiles of 8 or 16 (QDX_GEN_SMALL_TILES=0: off).
+    // Batches of at most one 32-row tile per resident warp (README-sized runs, the 65 536-row configurations) are latency
+    // problems: the kernel lasts as long as one warp needs for its tile, so the rows are spread evenly over ALL resident warps
+    // in tiles of ceil(rows per warp) rounded up to 4, at least 8 (QDX_GEN_SMALL_TILES=0: off).
     static int small_tiles = -1;
     if (small_tiles < 0) { const char* e_ = getenv("QDX_GEN_SMALL_TILES"); small_tiles = e_ ? atoi(e_) : 1; }
     int32_t tile_rows = generate_tile_rows(B, 0);
     const int64_t per_warp = (B + cap * QDX_GEN_WARPS - 1) / (cap * QDX_GEN_WARPS);
-    if (small_tiles && per_warp <= 16) tile_rows = per_warp <= 8 ? 8 : 16;
+    if (small_tiles && per_warp <= 32) { tile_rows = (int32_t)((per_warp + 3) / 4 * 4); if (tile_rows < 8) tile_rows = 8; }
     const int64_t g = (B + QDX_GEN_WARPS * tile_rows - 1) / (QDX_GEN_WARPS * tile_rows);
     *grid_out = (unsigned)(g < cap ? g : cap);
     *tile_rows_out = tile_rows;
