@@ -12,6 +12,7 @@
 //            (order_key(meta) << 32 | index).
 // Ranking on the squared distance and taking sqrt of the k survivors is exact: sqrt is monotone, so the
 // multiset of the k smallest distances is unchanged.
+#include <cstdlib>
 #include "qdx_common.cuh"
 #include "../../include/qdx.h"
 
@@ -158,7 +159,7 @@ static int qdx_rank_desc(const float* val, int64_t N, int64_t limit, int32_t* ou
 
 // ---- k-NN competition over FITNESS-SORTED candidates.  Row i competes only against j with f_i <= f_j: with the
 // candidates sorted by descending fitness those are a PREFIX of the array, so the pair space is a triangle -- half the
-// work of the dense scan -- and a CTA of 256 consecutive sorted rows shares one bound (the end of the ties of its last
+// work of the dense scan -- and a CTA of 128 consecutive sorted rows shares one bound (the end of the ties of its last
 // row).  The order in which candidates are visited does not matter: the result is the multiset of the k smallest
 // distances.  Inner loop: one LDS.128 per candidate (fitness + descriptor packed), the reference's subtract / square /
 // left-to-right sum, one fused predicate (closer than the current k-th; AND fitter only in the few tiles where the sorted
@@ -199,16 +200,24 @@ __device__ __forceinline__ void qdx_dns_scan_tile(const float4* __restrict__ s_c
     }
 }
 
+#ifndef QDX_DNS_ROWS
+#define QDX_DNS_ROWS 128         // query rows (= threads) per CTA
+#endif
 template <int KMAX, int DD>
-__global__ void __launch_bounds__(256) qdx_dns_knn_sorted_kernel(const float* __restrict__ sf, const float* __restrict__ sd,
+__global__ void __launch_bounds__(QDX_DNS_ROWS) qdx_dns_knn_sorted_kernel(const float* __restrict__ sf, const float* __restrict__ sd,
                                                                  const int32_t* __restrict__ perm, int64_t N, int32_t k,
                                                                  float* __restrict__ meta) {
+    constexpr int ROWS = QDX_DNS_ROWS;
     constexpr int TILE = 1024;
     __shared__ float4 s_c[TILE];                    // (d0, d1, fitness, d2)
     __shared__ float s_d3[DD == 4 ? TILE : 4];
     __shared__ long long s_bound, s_nnan;
-    const int64_t cta = (int64_t)gridDim.x - 1 - (int64_t)blockIdx.x;      // longest prefixes first
-    const int64_t r0 = cta * 256, r = r0 + threadIdx.x;
+    // (Measured, no gain: walking the odd rounds of CTAs backwards ("snake") to pair long prefixes with short ones on an SM --
+    //  2.53 vs 2.35 ms at 256 rows, 2.18 vs 2.19 at 128: the hardware does not deal CTAs to the SMs round-robin.  128 rows per
+    //  CTA instead of 256: 2.35 -> 2.18 ms, finer units for the block scheduler.  profiles/r2_notes.md)
+    const int64_t b = (int64_t)blockIdx.x;
+    const int64_t cta = (int64_t)gridDim.x - 1 - b;                        // longest prefixes first
+    const int64_t r0 = cta * ROWS, r = r0 + threadIdx.x;
     const bool valid = r < N;
     const float fi = valid ? sf[r] : -INFINITY;
     if (sf[r0] == -INFINITY) {                       // sorted descending: the whole CTA is empty slots (:144-145)
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(256) qdx_dns_knn_sorted_kernel(const float* __
         return;
     }
     if (threadIdx.x == 0) {                          // end of the ties of the CTA's last (lowest-fitness) row
-        const int64_t last = r0 + 255 < N - 1 ? r0 + 255 : N - 1;
+        const int64_t last = r0 + ROWS - 1 < N - 1 ? r0 + ROWS - 1 : N - 1;
         const uint32_t ok = qdx_order_key(sf[last]);
         int64_t lo = last + 1, hi = N;
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (qdx_order_key(sf[mid]) >= ok) lo = mid + 1; else hi = mid; }
@@ -328,6 +337,7 @@ int qdx_dns_add(const float* pop_genotypes, const float* pop_fitness, const floa
     QdxCat c{pop_fitness, pop_desc, batch_fitness, batch_desc, P, P + B, desc_dim};
     const int64_t N = P + B;
     const unsigned g256 = (unsigned)((N + 255) / 256);
+    const unsigned gknn = (unsigned)((N + QDX_DNS_ROWS - 1) / QDX_DNS_ROWS);
     if (desc_dim <= 4) {
         // candidates sorted by descending fitness (bucketed rank), then the triangular k-NN scan
         float* f_all = nullptr;
@@ -340,10 +350,10 @@ int qdx_dns_add(const float* pop_genotypes, const float* pop_fitness, const floa
             qdx_dns_sorted_gather_kernel<<<g256, 256, 0, st>>>(c, perm, sf, sd);
 #define QDX_DNS_SORTED(KM)                                                                                             \
     do {                                                                                                               \
-        if (desc_dim == 1) qdx_dns_knn_sorted_kernel<KM, 1><<<g256, 256, 0, st>>>(sf, sd, perm, N, k, meta_scratch);      \
-        else if (desc_dim == 2) qdx_dns_knn_sorted_kernel<KM, 2><<<g256, 256, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
-        else if (desc_dim == 3) qdx_dns_knn_sorted_kernel<KM, 3><<<g256, 256, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
-        else qdx_dns_knn_sorted_kernel<KM, 4><<<g256, 256, 0, st>>>(sf, sd, perm, N, k, meta_scratch);                    \
+        if (desc_dim == 1) qdx_dns_knn_sorted_kernel<KM, 1><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch);      \
+        else if (desc_dim == 2) qdx_dns_knn_sorted_kernel<KM, 2><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
+        else if (desc_dim == 3) qdx_dns_knn_sorted_kernel<KM, 3><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
+        else qdx_dns_knn_sorted_kernel<KM, 4><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch);                    \
     } while (0)
             if (k <= 4) QDX_DNS_SORTED(4);
             else if (k <= 16) QDX_DNS_SORTED(16);
