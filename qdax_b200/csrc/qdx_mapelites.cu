@@ -1190,6 +1190,9 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out, 
     int32_t tile_rows = generate_tile_rows(B, 0);
     const int64_t per_warp = (B + cap * QDX_GEN_WARPS - 1) / (cap * QDX_GEN_WARPS);
     if (small_tiles && per_warp <= 32) { tile_rows = (int32_t)((per_warp + 3) / 4 * 4); if (tile_rows < 8) tile_rows = 8; }
+    static int force_rows = -1;      // QDX_GEN_TILE_ROWS=n: timing experiments (tools/time_generate.py)
+    if (force_rows < 0) { const char* e_ = getenv("QDX_GEN_TILE_ROWS"); force_rows = e_ ? atoi(e_) : 0; }
+    if (force_rows >= 4 && force_rows <= 32) tile_rows = force_rows & ~3;
     const int64_t g = (B + QDX_GEN_WARPS * tile_rows - 1) / (QDX_GEN_WARPS * tile_rows);
     *grid_out = (unsigned)(g < cap ? g : cap);
     *tile_rows_out = tile_rows;
@@ -1205,7 +1208,9 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out, 
 //   same + end game: once less than one round of tiles is left, pieces of 8 / 16 rows fill a warp's 32-row tile before ONE
 //   scoring pass (round 2, gpurun_out/r2r_gen_*.json)                           110.2 / 193.0 / 688 us (8 rows), 100.0 / 182.9 / 686 (16)
 //                                                                          vs    98.6 / 176.9 / 680 us without, same run: the finer
-//   deal does not shorten the tail -- what is left at the end runs on SM sub-partitions with one or two warps, at their
+//   forced tile heights for every batch size (QDX_GEN_TILE_ROWS, gpurun_out/r2x_gen_*.json), 2^20 rows: 32 rows 673 us, 28: 707, 24: 735,
+//   20: 789, 16: 861 -- the lane = row phases cost ~28 % of a 32-row tile and do not shrink with its height.
+//   The finer deal does not shorten the tail -- what is left at the end runs on SM sub-partitions with one or two warps, at their
 //   latency-bound single-warp rate, however it is cut -- and pays a lane = row parent-selection pass per piece.
 // The tail of the kernel is the lowest-priority warp of every SM sub-partition finishing its last tile alone, at
 // single-warp issue rate; smaller last tiles shorten it but pay the fixed per-tile cost of the lane = row scoring phase.
