@@ -159,7 +159,7 @@ static int qdx_rank_desc(const float* val, int64_t N, int64_t limit, int32_t* ou
 
 // ---- k-NN competition over FITNESS-SORTED candidates.  Row i competes only against j with f_i <= f_j: with the
 // candidates sorted by descending fitness those are a PREFIX of the array, so the pair space is a triangle -- half the
-// work of the dense scan -- and a CTA of 128 consecutive sorted rows shares one bound (the end of the ties of its last
+// work of the dense scan -- and a CTA of 256 consecutive sorted rows shares one bound (the end of the ties of its last
 // row).  The order in which candidates are visited does not matter: the result is the multiset of the k smallest
 // distances.  Inner loop: one LDS.128 per candidate (fitness + descriptor packed), the reference's subtract / square /
 // left-to-right sum, one fused predicate (closer than the current k-th; AND fitter only in the few tiles where the sorted
@@ -201,20 +201,29 @@ __device__ __forceinline__ void qdx_dns_scan_tile(const float4* __restrict__ s_c
 }
 
 #ifndef QDX_DNS_ROWS
-#define QDX_DNS_ROWS 128         // query rows (= threads) per CTA
+#define QDX_DNS_ROWS 256         // query rows (= threads) per CTA
 #endif
 template <int KMAX, int DD>
 __global__ void __launch_bounds__(QDX_DNS_ROWS) qdx_dns_knn_sorted_kernel(const float* __restrict__ sf, const float* __restrict__ sd,
                                                                  const int32_t* __restrict__ perm, int64_t N, int32_t k,
-                                                                 float* __restrict__ meta) {
+                                                                 float* __restrict__ meta, float* __restrict__ partial,
+                                                                 unsigned* __restrict__ tickets) {
     constexpr int ROWS = QDX_DNS_ROWS;
+    // gridDim.y CTAs share a block of rows: CTA (x, y) scans the candidate tiles y, y + gridDim.y, ... of the block's prefix (an
+    // interleaved split halves every block's serial scan, long or short, and doubles the warps in flight); each keeps its own
+    // sorted k-list, the last one to finish (ticket) merges the lists -- the k smallest of a union are the k smallest of the
+    // parts' k smallest -- and writes the result.
+    const int ns = (int)gridDim.y, part = (int)blockIdx.y;
+    __shared__ bool s_merge;
     constexpr int TILE = 1024;
     __shared__ float4 s_c[TILE];                    // (d0, d1, fitness, d2)
     __shared__ float s_d3[DD == 4 ? TILE : 4];
     __shared__ long long s_bound, s_nnan;
-    // (Measured, no gain: walking the odd rounds of CTAs backwards ("snake") to pair long prefixes with short ones on an SM --
-    //  2.53 vs 2.35 ms at 256 rows, 2.18 vs 2.19 at 128: the hardware does not deal CTAs to the SMs round-robin.  128 rows per
-    //  CTA instead of 256: 2.35 -> 2.18 ms, finer units for the block scheduler.  profiles/r2_notes.md)
+    // (Measured, profiles/r2_notes.md section 5: the work of a CTA is proportional to its prefix and with one CTA per block of rows
+    //  the whole grid is resident at once, so the kernel lasts as long as the unluckiest SM -- 2.2 ... 3.6 ms from run to run.
+    //  Walking odd rounds of CTAs backwards to pair long with short prefixes did not help: the hardware does not deal CTAs
+    //  round-robin.  Splitting every block's tiles over 3 CTAs of 256 rows makes 1.33 waves of CTAs, the second of which fills
+    //  SMs as they drain: 1.92 ms, stable; sweep of rows 64 / 128 / 256 x split 1 ... 8 in the notes.)
     const int64_t b = (int64_t)blockIdx.x;
     const int64_t cta = (int64_t)gridDim.x - 1 - b;                        // longest prefixes first
     const int64_t r0 = cta * ROWS, r = r0 + threadIdx.x;
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(QDX_DNS_ROWS) qdx_dns_knn_sorted_kernel(const 
         const int64_t m = lo - s_nnan - 1;
         cnt = m < (int64_t)k ? (int)m : k;
     }
-    for (int64_t j0 = 0; j0 < bound; j0 += TILE) {
+    for (int64_t j0 = (int64_t)part * TILE; j0 < bound; j0 += (int64_t)ns * TILE) {
         const int n = (bound - j0) < TILE ? (int)(bound - j0) : TILE;
         const int n8 = (n + 7) & ~7;
         __syncthreads();
@@ -274,6 +283,34 @@ __global__ void __launch_bounds__(QDX_DNS_ROWS) qdx_dns_knn_sorted_kernel(const 
             if (j0 == self_tile) qdx_dns_scan_tile<KMAX, DD, true, true>(s_c, s_d3, n8, (int)(r - j0), fi, xi, top);
             else if (j0 < s_nnan || j0 + n > r0 || n8 != n) qdx_dns_scan_tile<KMAX, DD, false, true>(s_c, s_d3, n8, -1, fi, xi, top);
             else qdx_dns_scan_tile<KMAX, DD, false, false>(s_c, s_d3, n8, -1, fi, xi, top);
+        }
+    }
+    if (ns > 1) {
+        if (valid) {
+            float* mine = partial + ((int64_t)part * N + r) * KMAX;
+#pragma unroll
+            for (int u = 0; u < KMAX; ++u) mine[u] = top[u];
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_merge = atomicAdd(&tickets[cta], 1u) == (unsigned)(ns - 1);
+        __syncthreads();
+        if (!s_merge) return;
+        __threadfence();
+        if (threadIdx.x == 0) tickets[cta] = 0u;                                    // re-armed for the next call
+        if (valid) {
+            for (int h = 0; h < ns; ++h) {
+                if (h == part) continue;
+                const float* other = partial + ((int64_t)h * N + r) * KMAX;
+#pragma unroll
+                for (int u = 0; u < KMAX; ++u) {
+                    float w = __ldcg(other + u);
+                    if (w < top[KMAX - 1]) {
+#pragma unroll
+                        for (int q = 0; q < KMAX; ++q) { const float lo = fminf(top[q], w); w = fmaxf(top[q], w); top[q] = lo; }
+                    }
+                }
+            }
         }
     }
     if (!valid) return;
@@ -341,19 +378,26 @@ int qdx_dns_add(const float* pop_genotypes, const float* pop_fitness, const floa
     if (desc_dim <= 4) {
         // candidates sorted by descending fitness (bucketed rank), then the triangular k-NN scan
         float* f_all = nullptr;
-        cudaError_t e = cudaMallocAsync((void**)&f_all, sizeof(float) * (size_t)N * (2 + desc_dim) + sizeof(int32_t) * (size_t)N, st);
+        static int ns = -1;          // QDX_DNS_SPLIT=1: one CTA per block of rows (A/B)
+        if (ns < 0) { const char* e_ = getenv("QDX_DNS_SPLIT"); ns = e_ ? atoi(e_) : 3; if (ns < 1 || ns > 8) ns = 3; }
+        const int kmax = k <= 4 ? 4 : (k <= 16 ? 16 : 32);
+        const size_t part_floats = ns > 1 ? (size_t)ns * (size_t)N * (size_t)kmax : 0;
+        cudaError_t e = cudaMallocAsync((void**)&f_all, sizeof(float) * ((size_t)N * (2 + desc_dim) + part_floats) + sizeof(int32_t) * (size_t)N + sizeof(unsigned) * (size_t)gknn, st);
         if (e != cudaSuccess) return (int)e;
         float* sf = f_all + N; float* sd = sf + N; int32_t* perm = (int32_t*)(sd + N * desc_dim);
+        float* partial = (float*)(perm + N); unsigned* tickets = (unsigned*)(partial + part_floats);
+        e = cudaMemsetAsync(tickets, 0, sizeof(unsigned) * (size_t)gknn, st);
+        if (e != cudaSuccess) { cudaFreeAsync(f_all, st); return (int)e; }
         qdx_dns_cat_fit_kernel<<<g256, 256, 0, st>>>(c, f_all);
         int rc = qdx_rank_desc(f_all, N, N, perm, st);
         if (rc == 0) {
             qdx_dns_sorted_gather_kernel<<<g256, 256, 0, st>>>(c, perm, sf, sd);
 #define QDX_DNS_SORTED(KM)                                                                                             \
     do {                                                                                                               \
-        if (desc_dim == 1) qdx_dns_knn_sorted_kernel<KM, 1><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch);      \
-        else if (desc_dim == 2) qdx_dns_knn_sorted_kernel<KM, 2><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
-        else if (desc_dim == 3) qdx_dns_knn_sorted_kernel<KM, 3><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch); \
-        else qdx_dns_knn_sorted_kernel<KM, 4><<<gknn, QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch);                    \
+        if (desc_dim == 1) qdx_dns_knn_sorted_kernel<KM, 1><<<dim3(gknn, (unsigned)ns), QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch, partial, tickets);      \
+        else if (desc_dim == 2) qdx_dns_knn_sorted_kernel<KM, 2><<<dim3(gknn, (unsigned)ns), QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch, partial, tickets); \
+        else if (desc_dim == 3) qdx_dns_knn_sorted_kernel<KM, 3><<<dim3(gknn, (unsigned)ns), QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch, partial, tickets); \
+        else qdx_dns_knn_sorted_kernel<KM, 4><<<dim3(gknn, (unsigned)ns), QDX_DNS_ROWS, 0, st>>>(sf, sd, perm, N, k, meta_scratch, partial, tickets);                    \
     } while (0)
             if (k <= 4) QDX_DNS_SORTED(4);
             else if (k <= 16) QDX_DNS_SORTED(16);
