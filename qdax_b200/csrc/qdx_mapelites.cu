@@ -1210,6 +1210,9 @@ static int generate_grid(Kern kern, size_t smem, int64_t B, unsigned* grid_out, 
 //                                                                          vs    98.6 / 176.9 / 680 us without, same run: the finer
 //   forced tile heights for every batch size (QDX_GEN_TILE_ROWS, gpurun_out/r2x_gen_*.json), 2^20 rows: 32 rows 673 us, 28: 707, 24: 735,
 //   20: 789, 16: 861 -- the lane = row phases cost ~28 % of a 32-row tile and do not shrink with its height.
+//   grab for the NEXT tile issued at the start of the current one (the atomic's round trip hidden behind a tile of work): 2^20 rows
+//   679 -> 690 us, c2 (one tile per warp) 72 -> 105 us -- a warp that commits to its next tile a tile early takes it from a warp
+//   that would have been free sooner (gpurun_out/r3f_*).
 //   The finer deal does not shorten the tail -- what is left at the end runs on SM sub-partitions with one or two warps, at their
 //   latency-bound single-warp rate, however it is cut -- and pays a lane = row parent-selection pass per piece.
 // The tail of the kernel is the lowest-priority warp of every SM sub-partition finishing its last tile alone, at
