@@ -651,6 +651,29 @@ def run_gpu(args, cfg):
     hbm_peak, peak_src, _, _ = _peaks()
     ab = algorithmic_bytes(D, Dd)
     rl = kernel_rooflines(cfg, args.config, kern_ms, B, K, world, clocks["sm_mhz"] if clocks else None, added_last)
+    if world > 1:
+        # north_star: "as a fraction of the HBM / NVLink roofline".  What the reference-faithful exchange (all_gather of every
+        # offspring tuple, distributed_map_elites.py:133-141) would move per rank and generation, against what the active one moves.
+        nvlink_peak = 900.0                                   # GB/s per direction and GPU (NVLink 5 through NVSwitch, nominal)
+        per_off = 4 * D + 4 + 4 * Dd + 4
+        ag_bytes = (world - 1) * B * per_off                  # received by every rank
+        used = getattr(me, "_exchange", args.exchange)
+        ex = {"exchange": used, "bound": "nvlink" if used == "allgather" else "latency (system-scope atomics + winner rows over NVLink)",
+              "peak": nvlink_peak, "unit": "GB/s per direction", "peak_source": "nominal NVLink 5 per GPU",
+              "allgather_bytes_per_rank_per_generation": ag_bytes, "allgather_ms_at_peak": ag_bytes / (nvlink_peak * 1e9) * 1e3}
+        if used == "allgather" and "exchange" in kern_ms:
+            ex["achieved"] = ag_bytes / (kern_ms["exchange"] * 1e-3) / 1e9
+            ex["frac"] = ex["achieved"] / nvlink_peak
+        else:
+            # p2p / regen / winners: keys of improving offers (8 B x (R - 1) each), 8 key words + a flag per peer, and the rows of the
+            # elected winners owned by other ranks -- a few KB per generation in steady state
+            moved = added_last * (world - 1) / world * per_off + (world - 1) * (8 * 8 + 8) + 64 * (world - 1) * 8
+            ex["bytes_per_rank_per_generation_estimate"] = moved
+            ex["achieved"] = moved / (ms_total / args.steps * 1e-3) / 1e9
+            ex["frac"] = ex["achieved"] / nvlink_peak
+            ex["note"] = ("the exchange is not bandwidth-bound: it moves ~%.1f KB per rank and generation where the all-gather of the reference would "
+                          "move %.0f MB (%.2f ms at the NVLink peak, against a %.3f ms generation)" % (moved / 1e3, ag_bytes / 1e6, ex["allgather_ms_at_peak"], ms_total / args.steps))
+        rl["exchange"] = ex
     dom = max((k for k in kern_ms if k in ("generate", "cells")), key=lambda k: kern_ms[k])
     dom_bytes = ab["generate_per_offspring"] * B if dom == "generate" else (4 * Dd + 4) * B + K * Dd * 4
     dom_gbs = dom_bytes / (kern_ms[dom] * 1e-3) / 1e9
