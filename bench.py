@@ -466,7 +466,32 @@ def measure_config(name, args, dev, steps):
     m = torch.stack(keep).cpu()
     inserted = float(m[:, 3].sum())
     value = steps * cfg["B"] / (ms_total * 1e-3)
+    scan = None
+    if name == "c1":
+        # the README idiom: jax.lax.scan(map_elites.scan_update, ...) = MAPElites.scan; wall clock from the call to the final carry
+        # key and the stacked metrics on the host (README.md:121-140), 50 iterations, replayed as one CUDA graph
+        import time
+        n_it = 50
+        (rep, state, key), _ = me.scan((rep, state, key), n_it, donate=True)                    # one-time costs outside the timing
+        torch.cuda.synchronize()
+        loops = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            (rep, state, key), ms_ = me.scan((rep, state, key), n_it, donate=True)
+            host = {k: v.cpu() for k, v in ms_.items()}
+            loops.append(time.perf_counter() - t0)
+        t_loop = sorted(loops)[1]
+        (rep, state, key), _ = me.scan((rep, state, key), n_it, donate=True, graph=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        (rep, state, key), ms_ = me.scan((rep, state, key), n_it, donate=True, graph=True)     # captured again on every call
+        host = {k: v.cpu() for k, v in ms_.items()}
+        t_graph = time.perf_counter() - t0
+        scan = {"iterations": n_it, "api": "MAPElites.scan (= jax.lax.scan(scan_update)) + metrics to the host, wall clock",
+                "offspring_per_s": n_it * cfg["B"] / t_loop, "ms_per_iteration": t_loop / n_it * 1e3,
+                "graph_offspring_per_s_incl_capture": n_it * cfg["B"] / t_graph, "graph_ms_per_iteration_incl_capture": t_graph / n_it * 1e3}
     return {"config": _config_dict(args, cfg, cfg["B"], name=name, gpus=1), "value": value, "unit": UNIT, "ms_per_step": ms_total / steps, "steps": steps,
+            "readme_scan": scan,
             "kernel_ms": kern_ms, "host_enqueue_ms_per_step": host_ms, "insertions_per_s": inserted / (ms_total * 1e-3),
             "rooflines": kernel_rooflines(cfg, name, kern_ms, cfg["B"], K, 1, None, float(m[-1, 3])),
             "final": {"coverage": float(m[-1, 2]), "qd_score": float(m[-1, 0])},
