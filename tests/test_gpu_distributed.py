@@ -31,7 +31,7 @@ dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 N = lambda t: t.detach().cpu().numpy()
 
-def run(task, scoring, cent_t, B_dev, D, iters, exchange):
+def run(task, scoring, cent_t, B_dev, D, iters, exchange, donate=False):
     em = MixingEmitter(lambda x, k: x, functools.partial(isoline_variation, iso_sigma=0.05, line_sigma=0.1, minval=0.0, maxval=1.0), 1.0, B_dev)
     me = DistributedMAPElites(scoring, em, functools.partial(default_qd_metrics, qd_offset=0.0), exchange=exchange)
     init_all = qr.uniform(jr.key(11), (world * 16, D), device=dev)
@@ -47,7 +47,7 @@ def run(task, scoring, cent_t, B_dev, D, iters, exchange):
     okeys = [np.array(k) for k in keys]
     for it in range(iters):
         ks = qr.split(key); key, sub = ks[0], ks[1]
-        rep, state, m = me.update(rep, state, sub)
+        rep, state, m = me.update(rep, state, sub, donate=donate)
         subs = []
         for r in range(world):
             s2 = jr.split(okeys[r]); okeys[r] = s2[0]; subs.append(s2[1])
@@ -65,6 +65,10 @@ for exchange in ("allgather", "winners", "regen", "p2p"):
     run("arm", arm_scoring_function, grid, 300, 20, 4, exchange)
     cvt = torch.from_numpy(np.random.default_rng(0).random((500, 2)).astype(np.float32)).to(dev)
     run("rastrigin", rastrigin_scoring_function, cvt, 257, 100, 3, exchange)
+# soak: the bench path (donated repertoire, one C call per generation, peer-memory exchange with offspring blocks) for 40 generations,
+# checked against the oracle after every generation; a shard size that is not a multiple of the tile height
+grid = compute_euclidean_centroids((24, 24), 0.0, 1.0, device=dev)
+run("arm", arm_scoring_function, grid, 1000 + 8 * 3, 40, 40, "p2p", donate=True)
 dist.barrier()
 if rank == 0:
     print("DISTRIBUTED_OK", world)
@@ -72,7 +76,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_distributed_map_elites_nccl(tmp_path, world):
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} CUDA devices")
