@@ -566,6 +566,8 @@ def run_gpu(args, cfg):
                   "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", **{k: v for k, v in r.items() if k not in ("value", "unit", "ms_per_step", "steps")}})
         return
 
+    if args.weak and world > 1:          # weak scaling (not the BASELINE configuration): every rank keeps the 1-GPU batch
+        cfg = dict(cfg, B=cfg["B"] * world, note=cfg["note"] + " -- WEAK scaling variant: batch x N GPUs")
     D, task, B_total = cfg["D"], cfg["task"], cfg["B"]
     assert B_total % world == 0
     B = B_total // world
@@ -737,7 +739,7 @@ def run_gpu(args, cfg):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if (args.weak and world > 1) else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": _config_dict(args, cfg, B_step=B_total),
         "timed_api": ("MAPElites.update" if world == 1 else "DistributedMAPElites.update") + "(repertoire, emitter_state, key, donate=True), host key chain",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / e2e_steps,
@@ -885,6 +887,7 @@ def main():
     ap.add_argument("--no-insert-probe", action="store_true", help="skip the large-row insert-kernel measurement (N=1 only)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip c1 / c2 / c4 / c5 (N=1 only)")
     ap.add_argument("--no-oracle-parity", action="store_true")
+    ap.add_argument("--weak", action="store_true", help="N > 1: keep the 1-GPU batch per rank (weak scaling; not the BASELINE configuration)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
