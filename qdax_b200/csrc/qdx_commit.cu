@@ -51,6 +51,9 @@ constexpr int JB = QDX_COMMIT_JB;      // most list entries (changed cells) per 
 #ifndef QDX_COMMIT_CHUNK
 #define QDX_COMMIT_CHUNK 4096
 #endif
+#ifndef QDX_COMMIT_OWN_HALF
+#define QDX_COMMIT_OWN_HALF 1  // A/B switch: 0 = every winner goes through the grid-wide list (round-1 behaviour)
+#endif
 #ifndef QDX_COMMIT_EXP
 #define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
 #endif
@@ -248,6 +251,12 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
 
         // ---- phase 1, thread = cell: election result, fitness / descriptor, key reset, metrics, occupancy; the changed
         // cells of the whole grid are appended to ONE global list (warp-aggregated atomics) that phase 2 deals out
+        // A warp keeps the first half of its own winners (cell, source row in registers) and starts streaming them the moment its
+        // CTA has arrived at the grid barrier, instead of waiting for the slowest CTA's phase 1 (~2 us of 9 before the first row
+        // moved); only the other half goes on the grid-wide list, whose guided deal evens out what the static half leaves uneven.
+        // (One slab of cells per CTA only: K <= 128 cells x CTAs.)
+        const bool own_half = (c_hi - c_lo) <= (int64_t)(CW * 32) && QDX_COMMIT_OWN_HALF;
+        int32_t st_cell = 0, st_src = 0; unsigned st_mask = 0u;
         int occ_after = 0, slab_i = 0;
         for (int64_t slab = c_lo; slab < c_hi; slab += CW * 32, ++slab_i) {
             const int64_t c = slab + tid;
@@ -279,11 +288,18 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             const unsigned ob = __ballot_sync(0xffffffffu, in && fcell != -INFINITY);
             if (keep_bits && lane == 0) s_occ[slab_i * CW + wid] = ob;
             occ_after += __popc(ob);
-            const unsigned wb = __ballot_sync(0xffffffffu, i >= 0);
+            unsigned wb = __ballot_sync(0xffffffffu, i >= 0);
+            if (own_half) {
+                const int keep = __popc(wb) / 2;
+                const bool mine = i >= 0 && __popc(wb & ((1u << lane) - 1u)) < keep;
+                st_mask = __ballot_sync(0xffffffffu, mine);
+                if (mine) { st_cell = (int32_t)c; st_src = (int32_t)i; }
+                wb &= ~st_mask;
+            }
             unsigned base = 0;
             if (lane == 0 && wb) base = atomicAdd(&ws->job_count, (unsigned)__popc(wb));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (i >= 0) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
+            if ((wb >> lane) & 1u) { const unsigned pos = base + __popc(wb & ((1u << lane) - 1u)); job_cell[pos] = (int32_t)c; job_src[pos] = (int32_t)i; }
         }
         // ---- this CTA's partial metrics and occupied count, published BEFORE the grid barrier: the service CTA sums them
         // while the rows stream
@@ -308,17 +324,62 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
                 __threadfence();                              // ONE fence: partials + job list before the count and the arrival
                 if (tail) *(volatile unsigned long long*)&ws->occ_pub[blockIdx.x] = ((unsigned long long)seq << 32) | (uint32_t)t;
                 atomicAdd(&ws->cta_arrived, 1u);
-                unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
-                    unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
-                }
-                __threadfence();
             }
+        }
+        // ---- the row copies: the rows never touch registers -- one lane per warp drives a ring of shared-memory stages with the
+        // bulk-copy engine (global -> shared on an mbarrier, then shared -> global)
+        const uint32_t rowbytes = (uint32_t)p.D * 4u;
+        const bool bulk = (p.D & 3) == 0;
+        const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
+        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
+        uint64_t* bars = &s_bar[wid * NST];
+        unsigned long long* sdst = &s_dst[wid * NST];
+        uint32_t* sby = &s_bytes[wid * NST];
+        uint32_t ql = 0, qs = 0;                                            // lane 0: pieces loaded / stored so far (ring positions)
+        auto stream_row = [&](int32_t cell, int32_t src) {
+            if (bulk) {
+                if (lane == 0) {
+                    for (int pc = 0; pc < pieces; ++pc) {
+                        if (ql - qs >= (uint32_t)LEAD) {          // piece qs has been in flight long enough: send it on
+                            const uint32_t sl = qs % NST;
+                            mbar_wait(&bars[sl], (qs / NST) & 1u);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
+                            ++qs;
+                        }
+                        const uint32_t sl = ql % NST;
+                        const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
+                        asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");   // stage free again
+                        sdst[sl] = (unsigned long long)((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK);
+                        sby[sl] = bytes;
+                        mbar_expect_tx(&bars[sl], bytes);
+                        bulk_g2s(my_stage + sl * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes, &bars[sl]);
+                        ++ql;
+                    }
+                }
+                __syncwarp();
+            } else {                                                  // D not a multiple of 4: plain per-lane copy
+                const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
+                for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
+            }
+        };
+        if (QDX_COMMIT_EXP != 2)
+            for (unsigned m = st_mask; m; m &= m - 1u) {              // this warp's own half: no list, no barrier
+                const int l = __ffs(m) - 1;
+                stream_row(__shfl_sync(0xffffffffu, st_cell, l), __shfl_sync(0xffffffffu, st_src, l));
+            }
+        // ---- the grid barrier (all CTAs are co-resident: cooperative launch): the job list is complete
+        if (wid == 0 && lane == 0) {
+            unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*(volatile unsigned*)&ws->cta_arrived < (unsigned)nblk) {
+                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) { qdx_set_error(ws, QDX_ERR_INTERNAL); break; }
+            }
+            __threadfence();
         }
         __syncthreads();
         QDX_TRACE_MAX(3);                                     // last CTA through the grid barrier
-        const bool aborted = *(volatile int32_t*)&ws->error == QDX_ERR_INTERNAL;    // a grid-barrier wait timed out: stream nothing
+        const bool aborted = *(volatile int32_t*)&ws->error == QDX_ERR_INTERNAL;    // a grid-barrier wait timed out: stream nothing more
 
         // ---- phase 2: the row copies, dealt out in batches of list entries.  SMs differ in their distance to the memory
         // they read and write, so a static deal leaves the slow ones streaming long after the fast ones are done (measured:
@@ -328,9 +389,6 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
         // The grab for the next batch is issued when a batch starts and consumed after its first row, and that batch's
         // list entries are fetched by the lanes then -- both latencies sit behind row traffic already in flight.
         const unsigned njobs = (QDX_COMMIT_EXP == 2 || aborted) ? 0u : *(volatile unsigned*)&ws->job_count;
-        const uint32_t rowbytes = (uint32_t)p.D * 4u;
-        const bool bulk = (p.D & 3) == 0;
-        const int pieces = (int)((rowbytes + CHUNK - 1) / CHUNK);
         const unsigned g = blockIdx.x * CW + wid, G = (unsigned)nblk * CW;
         unsigned J0 = (njobs + GS * G - 1u) / (GS * G);                     // static first batch: about half of the list
         J0 = J0 < 1u ? 1u : (J0 > (unsigned)JB ? (unsigned)JB : J0);
@@ -340,11 +398,6 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
         unsigned cur_base = g * J0, cur_n = cur_base < njobs ? (njobs - cur_base < J0 ? njobs - cur_base : J0) : 0u;
         int32_t my_cell = 0, my_src = 0;
         if ((unsigned)lane < cur_n) { my_cell = __ldcg(job_cell + cur_base + lane); my_src = __ldcg(job_src + cur_base + lane); }
-        unsigned char* my_stage = s_stage + (size_t)wid * NST * CHUNK;
-        uint64_t* bars = &s_bar[wid * NST];
-        unsigned long long* sdst = &s_dst[wid * NST];
-        uint32_t* sby = &s_bytes[wid * NST];
-        uint32_t ql = 0, qs = 0;                                            // lane 0: pieces loaded / stored so far (ring positions)
         while (cur_n > 0u) {
             unsigned nxt_base = 0xFFFFFFFFu, nxt_n = 0u;
             if (dyn && lane == 0) {
@@ -356,32 +409,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             }
             int32_t nx_cell = 0, nx_src = 0;
             for (unsigned e = 0; e < cur_n; ++e) {
-                const int32_t cell = __shfl_sync(0xffffffffu, my_cell, (int)e), src = __shfl_sync(0xffffffffu, my_src, (int)e);
-                if (bulk) {
-                    if (lane == 0) {
-                        for (int pc = 0; pc < pieces; ++pc) {
-                            if (ql - qs >= (uint32_t)LEAD) {          // piece qs has been in flight long enough: send it on
-                                const uint32_t sl = qs % NST;
-                                mbar_wait(&bars[sl], (qs / NST) & 1u);
-                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                                if (QDX_COMMIT_EXP != 1) bulk_s2g((void*)sdst[sl], my_stage + sl * CHUNK, sby[sl]);
-                                ++qs;
-                            }
-                            const uint32_t sl = ql % NST;
-                            const uint32_t bytes = rowbytes - (uint32_t)pc * CHUNK < (uint32_t)CHUNK ? rowbytes - (uint32_t)pc * CHUNK : (uint32_t)CHUNK;
-                            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NST - LEAD) : "memory");   // stage free again
-                            sdst[sl] = (unsigned long long)((char*)p.rep_g + ((int64_t)cell * p.D) * 4 + (int64_t)pc * CHUNK);
-                            sby[sl] = bytes;
-                            mbar_expect_tx(&bars[sl], bytes);
-                            bulk_g2s(my_stage + sl * CHUNK, (const char*)p.off_g + ((int64_t)src * p.D) * 4 + (int64_t)pc * CHUNK, bytes, &bars[sl]);
-                            ++ql;
-                        }
-                    }
-                    __syncwarp();
-                } else {                                                  // D not a multiple of 4: plain per-lane copy
-                    const float* srow = p.off_g + (int64_t)src * p.D; float* drow = p.rep_g + (int64_t)cell * p.D;
-                    for (int d = lane; d < p.D; d += 32) drow[d] = srow[d];
-                }
+                stream_row(__shfl_sync(0xffffffffu, my_cell, (int)e), __shfl_sync(0xffffffffu, my_src, (int)e));
                 if (e == 0u && dyn) {
                     nxt_base = __shfl_sync(0xffffffffu, nxt_base, 0); nxt_n = __shfl_sync(0xffffffffu, nxt_n, 0);
                     est = nxt_base + nxt_n;

@@ -442,6 +442,7 @@ def test_add_golden_injected(dev, golden, tb):
 # D = 1040 rows travel in two bulk pieces, D = 6 / 1 take the per-lane copy (rows not 16-byte multiples)
 @pytest.mark.parametrize("B,K,D,levels", [(50000, 10000, 100, 5), (100, 10000, 100, 1000), (65536, 100, 8, 3), (1, 4, 4, 1), (4096, 2500, 12, 2),
                                           (3000, 14400, 8, 50), (20000, 57600, 4, 10), (30000, 250000, 4, 10), (600, 100, 1040, 4),
+                                          (9000, 14400, 512, 6), (20000, 57600, 260, 10), (40000, 50176, 300, 3),
                                           (500, 100, 6, 4), (300, 64, 1, 3)])
 @pytest.mark.parametrize("tb", ["first", "last"])
 def test_add_injected_random(dev, co, B, K, D, levels, tb):
