@@ -54,6 +54,9 @@ constexpr int JB = QDX_COMMIT_JB;      // most list entries (changed cells) per 
 #ifndef QDX_COMMIT_OWN_HALF
 #define QDX_COMMIT_OWN_HALF 1  // A/B switch: 0 = every winner goes through the grid-wide list (round-1 behaviour)
 #endif
+#ifndef QDX_COMMIT_OWN_NUM
+#define QDX_COMMIT_OWN_NUM 2   // quarters of a warp's winners kept by the warp
+#endif
 #ifndef QDX_COMMIT_EXP
 #define QDX_COMMIT_EXP 0      // timing experiments only: 1 = loads without stores, 2 = no row traffic at all
 #endif
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(CW * 32) qdx_commit_stream_kernel(const Commit
             occ_after += __popc(ob);
             unsigned wb = __ballot_sync(0xffffffffu, i >= 0);
             if (own_half) {
-                const int keep = __popc(wb) / 2;
+                const int keep = __popc(wb) * QDX_COMMIT_OWN_NUM / 4;
                 const bool mine = i >= 0 && __popc(wb & ((1u << lane) - 1u)) < keep;
                 st_mask = __ballot_sync(0xffffffffu, mine);
                 if (mine) { st_cell = (int32_t)c; st_src = (int32_t)i; }
