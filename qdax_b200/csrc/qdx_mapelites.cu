@@ -272,7 +272,9 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
         const uint32_t qmagic = (1u << 20) / (uint32_t)q + 1u;   // qi / q == (qi * qmagic) >> 20 for qi * q < 2^20
         // ---- phase 1: gene-parallel variation over the tile ---------------------------------------------
         // All 32 lanes stay converged (lanes past the end recompute the last quad and skip the store), so the
-        // normal transform can vote with a full mask.  (Measured, no gain: 2x unrolling (profiles/r1_notes.md); a software
+        // normal transform can vote with a full mask.  (Measured, no gain: prefetch.global.L2 of the next iteration's parent quads
+        // when the repertoire is larger than L2 (c4: 200 MB) -- 0.460 vs 0.463 ms, and +4 % at c3 when forced (gpurun_out/r3s_*);
+        // 2x unrolling (profiles/r1_notes.md); a software
         // pipeline that issues the NEXT quad's Threefry blocks next to the current quad's float transforms, to mix ALU- and
         // FMA-pipe work inside one warp: 0.710 vs 0.680 ms -- ptxas keeps the two streams apart, co-resident warps already
         // mix them (profiles/r2_notes.md).)
