@@ -1409,7 +1409,13 @@ static int generate_impl(const float* rep_genotypes, const float* rep_fitness, c
     p.rep_g = rep_genotypes; p.rep_f = rep_fitness; p.centroids = centroids; p.ws = ws;
     p.B = B; p.K = K; p.D = (int32_t)D;
     // chunk of genes staged per warp tile: whole row when it fits 16 KB per warp, else 128 genes
-    p.DC = (D <= 128) ? (int32_t)D : 128;
+    // genes per staged chunk: the whole row up to 128 genes; longer rows in chunks of 100 -- a 32-row tile of 100 floats per row
+    // (stride 100, 100 / 4 odd: conflict-free) is 12.8 KB per warp, 4 CTAs per SM, where 128-gene chunks (stride 132) allowed
+    // 3: 444 instead of 592 resident CTAs turned the 65 536-row batch of configuration c4 into 1.15 waves of 32-row tiles
+    // (generate 0.455 -> 0.407 ms, gpurun_out/r3u_*; chunks of 64: 0.415).  QDX_GEN_CHUNK=n overrides (A/B).
+    static int chunk = -1;
+    if (chunk < 0) { const char* e_ = getenv("QDX_GEN_CHUNK"); chunk = e_ ? atoi(e_) : 100; if (chunk < 8 || chunk > 128 || (chunk & 3)) chunk = 100; }
+    p.DC = (D <= 128) ? (int32_t)D : (desc_dim <= chunk ? chunk : 128);
     p.DS = ((p.DC & 7) == 4) ? p.DC : p.DC + 4;
     if (task == QDX_TASK_ARM && D > p.DC) return QDX_ERR_UNSUPPORTED;   // arm needs the whole row for its two passes
     p.out_xchg = (flags & QDX_GEN_OUT_XCHG) ? 1 : 0;
