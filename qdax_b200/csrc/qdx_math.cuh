@@ -143,12 +143,101 @@ QDX_DEV float qdx_normal_from_bits_t(uint32_t bits) {
     return 0x1.6a09e6p+0f * qdx_erfinvf_t<false, FULLWARP>(u);   // u in [lo, 1): |u| == 1 impossible
 }
 QDX_DEV float qdx_normal_from_bits(uint32_t bits) { return qdx_normal_from_bits_t<false>(bits); }
+// ---- packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2, PTX add / sub / mul / fma .rn.f32x2): two IEEE round-to-nearest
+// results per issued instruction.  Each element sees exactly the operation the scalar code performs, so the results are
+// bit-identical; the kernels that use them are bound by instruction issue, not by the FMA pipe.  (-DQDX_PACKED_F32=0: scalar.)
+#ifndef QDX_PACKED_F32
+#define QDX_PACKED_F32 1
+#endif
+struct QdxF2 { unsigned long long v; };
+QDX_DEV QdxF2 qdx_f2(float a, float b) { QdxF2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+QDX_DEV QdxF2 qdx_f2(float a) { return qdx_f2(a, a); }
+QDX_DEV void qdx_f2_get(QdxF2 x, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+QDX_DEV QdxF2 operator+(QdxF2 a, QdxF2 b) { QdxF2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+QDX_DEV QdxF2 operator-(QdxF2 a, QdxF2 b) { QdxF2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+QDX_DEV QdxF2 operator*(QdxF2 a, QdxF2 b) { QdxF2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+QDX_DEV QdxF2 qdx_fma2(QdxF2 a, QdxF2 b, QdxF2 c) { QdxF2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+// qdx_logf on a pair (the integer decomposition stays scalar)
+QDX_DEV QdxF2 qdx_logf2(float t0, float t1) {
+    const uint32_t i0 = __float_as_uint(t0) - 0x3f3504f3u, i1 = __float_as_uint(t1) - 0x3f3504f3u;
+    const int e0 = (int32_t)i0 >> 23, e1 = (int32_t)i1 >> 23;
+    const QdxF2 m = qdx_f2(__uint_as_float((i0 & 0x007fffffu) + 0x3f3504f3u), __uint_as_float((i1 & 0x007fffffu) + 0x3f3504f3u));
+    const QdxF2 r = m - qdx_f2(1.0f);
+    const QdxF2 z = r * r;
+    QdxF2 p = qdx_f2(7.0376836292E-2f);
+    p = qdx_fma2(p, r, qdx_f2(-1.1514610310E-1f));
+    p = qdx_fma2(p, r, qdx_f2(1.1676998740E-1f));
+    p = qdx_fma2(p, r, qdx_f2(-1.2420140846E-1f));
+    p = qdx_fma2(p, r, qdx_f2(1.4249322787E-1f));
+    p = qdx_fma2(p, r, qdx_f2(-1.6668057665E-1f));
+    p = qdx_fma2(p, r, qdx_f2(2.0000714765E-1f));
+    p = qdx_fma2(p, r, qdx_f2(-2.4999993993E-1f));
+    p = qdx_fma2(p, r, qdx_f2(3.3333331174E-1f));
+    QdxF2 y = (p * r) * z;
+    const QdxF2 fe = qdx_f2((float)e0, (float)e1);
+    y = qdx_fma2(fe, qdx_f2(-2.12194440e-4f), y);
+    y = qdx_fma2(z, qdx_f2(-0.5f), y);
+    QdxF2 res = r + y;
+    res = qdx_fma2(fe, qdx_f2(0.693359375f), res);
+    return res;
+}
+// qdx_log1pf on a pair.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it does not for the scalar .rn forms), which
+// changes the rounding: wherever the spec has a product feeding a sum, the product (or the sum) is done in scalar instructions.
+QDX_DEV void qdx_log1pf2(float y0, float y1, float& l0, float& l1) {
+    const QdxF2 y = qdx_f2(y0, y1);
+    const QdxF2 t = qdx_f2(1.0f) + y;
+    const QdxF2 a = y - (t - qdx_f2(1.0f)), b = qdx_f2(2.0f) - t;
+    float t0, t1, a0, a1, b0, b1, g0, g1;
+    qdx_f2_get(t, t0, t1); qdx_f2_get(a, a0, a1); qdx_f2_get(b, b0, b1);
+    qdx_f2_get(qdx_logf2(t0, t1), g0, g1);
+    const float c0 = a0 * b0, c1 = a1 * b1;
+    l0 = g0 + c0; l1 = g1 + c1;
+}
+// qdx_erfinv_central_poly on a pair
+QDX_DEV QdxF2 qdx_erfinv_central_poly2(QdxF2 w) {
+    w = w - qdx_f2(2.5f);
+    QdxF2 p = qdx_f2(2.81022636e-08f);
+    p = qdx_fma2(p, w, qdx_f2(3.43273939e-07f));
+    p = qdx_fma2(p, w, qdx_f2(-3.5233877e-06f));
+    p = qdx_fma2(p, w, qdx_f2(-4.39150654e-06f));
+    p = qdx_fma2(p, w, qdx_f2(0.00021858087f));
+    p = qdx_fma2(p, w, qdx_f2(-0.00125372503f));
+    p = qdx_fma2(p, w, qdx_f2(-0.00417768164f));
+    p = qdx_fma2(p, w, qdx_f2(0.246640727f));
+    p = qdx_fma2(p, w, qdx_f2(1.50140941f));
+    return p;
+}
+
 // Four normals from four draws, all 32 lanes converged: the Threefry blocks that produced `bits`, the uniform -> w
 // transforms and (when all 128 draws of the warp are central, 68 % of the time) the four Horner chains are straight-line
 // code with four independent dependency chains -- the per-draw version is one serial chain with a branch per draw.
 // Same operations per draw, so the results are bit-identical to qdx_normal_from_bits.
 QDX_DEV void qdx_normal4_from_bits(const uint32_t bits[4], float out[4]) {
     const float lo = -0x1.fffffep-1f;
+#if QDX_PACKED_F32
+    float u[4], w[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const QdxF2 f = qdx_f2(qdx_unit_float(bits[2 * h]), qdx_unit_float(bits[2 * h + 1]));
+        const QdxF2 v = f * qdx_f2(2.0f) + qdx_f2(lo);
+        float v0, v1; qdx_f2_get(v, v0, v1);
+        u[2 * h] = v0 < lo ? lo : v0; u[2 * h + 1] = v1 < lo ? lo : v1;
+        float l0, l1;
+        qdx_log1pf2(-(u[2 * h] * u[2 * h]), -(u[2 * h + 1] * u[2 * h + 1]), l0, l1);     // the squares in scalar: see qdx_log1pf2
+        w[2 * h] = -l0; w[2 * h + 1] = -l1;
+    }
+    const bool central2 = (w[0] < 5.0f) & (w[1] < 5.0f) & (w[2] < 5.0f) & (w[3] < 5.0f);
+    if (__all_sync(0xffffffffu, central2)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const QdxF2 r = qdx_f2(0x1.6a09e6p+0f) * (qdx_erfinv_central_poly2(qdx_f2(w[2 * h], w[2 * h + 1])) * qdx_f2(u[2 * h], u[2 * h + 1]));
+            qdx_f2_get(r, out[2 * h], out[2 * h + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = 0x1.6a09e6p+0f * (qdx_erfinv_poly<true>(w[j]) * u[j]);
+    }
+#else
     float u[4], w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -165,6 +254,7 @@ QDX_DEV void qdx_normal4_from_bits(const uint32_t bits[4], float out[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) out[j] = 0x1.6a09e6p+0f * (qdx_erfinv_poly<true>(w[j]) * u[j]);
     }
+#endif
 }
 // sin & cos: 3-term Cody-Waite by pi/2 (fused), minimax kernels on [-pi/4, pi/4].
 QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
