@@ -378,7 +378,7 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
                     }
                     float sj[4], cj[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) qdx_sincosf(thj[j], sj[j], cj[j]);   // 4 independent evaluations (ILP)
+                    for (int j = 0; j < 4; j += 2) qdx_sincosf2(thj[j], thj[j + 1], sj[j], cj[j], sj[j + 1], cj[j + 1]);   // two packed pairs (ILP)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { cs = cs + cj[j]; sn = sn + sj[j]; }
                 }
@@ -400,15 +400,19 @@ __device__ __forceinline__ void qdx_generate_body(const QdxGenParams& p) {
                 for (int d = 0; d < dc; d += 4) {
                     float4 v = *reinterpret_cast<const float4*>(xr + d);
                     float xs[4] = {v.x, v.y, v.z, v.w};
-                    float term[4];
+                    float term[4], xx[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float x = xs[j] * 10.0f - 5.0f;
-                        term[j] = x * x;
-                        if (TASK == QDX_TASK_RASTRIGIN) {
-                            float s, c;
-                            qdx_sincosf(0x1.921fb6p+2f * x, s, c);
-                            term[j] = term[j] - 10.0f * c;
+                        xx[j] = xs[j] * 10.0f - 5.0f;
+                        term[j] = xx[j] * xx[j];
+                    }
+                    if (TASK == QDX_TASK_RASTRIGIN) {
+#pragma unroll
+                        for (int j = 0; j < 4; j += 2) {       // two packed pairs
+                            float s0, c0, s1, c1;
+                            qdx_sincosf2(0x1.921fb6p+2f * xx[j], 0x1.921fb6p+2f * xx[j + 1], s0, c0, s1, c1);
+                            term[j] = term[j] - 10.0f * c0;
+                            term[j + 1] = term[j + 1] - 10.0f * c1;
                         }
                     }
 #pragma unroll

@@ -275,6 +275,35 @@ QDX_DEV void qdx_sincosf(float th, float& s_out, float& c_out) {
     s_out = sv; c_out = cv;
 }
 
+// qdx_sincosf on a pair: the reduction and the two minimax kernels on packed FP32 (every sum sits inside an FMA, so nothing here
+// can be contracted differently from the scalar code); rounding to the quadrant, the quadrant selects and the signs stay scalar.
+QDX_DEV void qdx_sincosf2(float th0, float th1, float& s0, float& c0, float& s1, float& c1) {
+#if QDX_PACKED_F32
+    const float q0 = rintf(th0 * 0x1.45f306p-1f), q1 = rintf(th1 * 0x1.45f306p-1f);
+    const QdxF2 q = qdx_f2(q0, q1);
+    QdxF2 r = qdx_fma2(q, qdx_f2(-0x1.921fb6p+0f), qdx_f2(th0, th1));
+    r = qdx_fma2(q, qdx_f2(0x1.777a5cp-25f), r);
+    r = qdx_fma2(q, qdx_f2(0x1.ee59dap-50f), r);
+    const QdxF2 s = r * r;
+    const QdxF2 ps = qdx_fma2(qdx_fma2(qdx_f2(-1.9515295891E-4f), s, qdx_f2(8.3321608736E-3f)), s, qdx_f2(-1.6666654611E-1f));
+    const QdxF2 sr = qdx_fma2(r * s, ps, r);
+    const QdxF2 pc = qdx_fma2(qdx_fma2(qdx_f2(2.443315711809948E-5f), s, qdx_f2(-1.388731625493765E-3f)), s, qdx_f2(4.166664568298827E-2f));
+    const QdxF2 cr = qdx_fma2(s * s, pc, qdx_fma2(s, qdx_f2(-0.5f), qdx_f2(1.0f)));
+    float sr0, sr1, cr0, cr1;
+    qdx_f2_get(sr, sr0, sr1); qdx_f2_get(cr, cr0, cr1);
+    const int n0 = (int)q0 & 3, n1 = (int)q1 & 3;
+    float sv0 = (n0 & 1) ? cr0 : sr0, cv0 = (n0 & 1) ? sr0 : cr0;
+    float sv1 = (n1 & 1) ? cr1 : sr1, cv1 = (n1 & 1) ? sr1 : cr1;
+    if (n0 & 2) sv0 = -sv0;
+    if ((n0 + 1) & 2) cv0 = -cv0;
+    if (n1 & 2) sv1 = -sv1;
+    if ((n1 + 1) & 2) cv1 = -cv1;
+    s0 = sv0; c0 = cv0; s1 = sv1; c1 = cv1;
+#else
+    qdx_sincosf(th0, s0, c0); qdx_sincosf(th1, s1, c1);
+#endif
+}
+
 // exp(z): n = rint(z*log2e), two-term fused reduction by ln2, degree-6 polynomial, two-step scaling by 2^n
 QDX_DEV float qdx_expf(float z) {
     if (z != z) return z;
