@@ -208,6 +208,8 @@ QDX_DEV QdxF2 qdx_erfinv_central_poly2(QdxF2 w) {
     return p;
 }
 
+// (Measured, not kept: evaluating BOTH erfinv polynomials on packed pairs in mixed warps and selecting per element -- bit-identical,
+//  c3 0.6465 -> 0.654 ms: the per-lane coefficient selects of the scalar mixed path are cheaper than a second polynomial.)
 // Four normals from four draws, all 32 lanes converged: the Threefry blocks that produced `bits`, the uniform -> w
 // transforms and (when all 128 draws of the warp are central, 68 % of the time) the four Horner chains are straight-line
 // code with four independent dependency chains -- the per-draw version is one serial chain with a branch per draw.
