@@ -177,9 +177,19 @@ __device__ __forceinline__ void qdx_dns_scan_tile(const float4* __restrict__ s_c
             float4 c;                                                           // (d0, d1, fitness, d2): d0 / d1 are one aligned LDS.64
             if (CHECK || DD >= 3) c = s_c[t + u];
             else { const float2 d01 = *reinterpret_cast<const float2*>(&s_c[t + u]); c = make_float4(d01.x, d01.y, 0.0f, 0.0f); }
-            float df = xi[0] - c.x;
-            float acc = df * df;
-            if (DD >= 2) { df = xi[1] - c.y; acc = acc + df * df; }
+            float acc, df;
+            if (DD == 2 && QDX_PACKED_F32) {
+                // both coordinates at once (FADD2 / FMUL2: two IEEE results per instruction, the kernel is issue-bound); the sum of
+                // the two rounded squares stays a scalar add -- ptxas would contract a packed product feeding a packed sum
+                const QdxF2 dd = qdx_f2(xi[0], xi[1]) - qdx_f2(c.x, c.y);
+                float s0, s1;
+                qdx_f2_get(dd * dd, s0, s1);
+                acc = s0 + s1;
+            } else {
+                df = xi[0] - c.x;
+                acc = df * df;
+                if (DD >= 2) { df = xi[1] - c.y; acc = acc + df * df; }
+            }
             if (DD >= 3) { df = xi[2] - c.w; acc = acc + df * df; }
             if (DD >= 4) { df = xi[3] - s_d3[t + u]; acc = acc + df * df; }
             v[u] = acc;
