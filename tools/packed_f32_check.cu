@@ -1,5 +1,5 @@
 // Packed-FP32 (FADD2 / FMUL2 / FFMA2) normal transform against the scalar one, bit for bit, on 16.7 M Threefry draws (needs a GPU):
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -fmad=false tools/packed_f32_check.cu -o /tmp/packed_f32_check \&\& /tmp/packed_f32_check
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -fmad=false tools/packed_f32_check.cu -o /tmp/packed_f32_check && /tmp/packed_f32_check
 // (how the ptxas contraction of mul.rn.f32x2 + add.rn.f32x2 was found: profiles/r2_notes.md section 1)
 #include <cstdio>
 #include "../qdax_b200/csrc/qdx_math.cuh"
